@@ -1,0 +1,741 @@
+// Engine: weights, scratch memory, the encoder / decoder / generate schedules and the C ABI
+// declared in include/hmocr.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gemm.cuh"
+#include "hmocr.h"
+#include "kernels.cuh"
+
+#define HM_API extern "C" __attribute__((visibility("default")))
+
+namespace hmocr {
+
+thread_local long g_launch_count = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+constexpr int IMG_H = 96, IMG_W = 320, MEM_S = 30, SWIN_OUT = 768;
+constexpr int DEPTHS[4] = {2, 2, 6, 2};
+constexpr int HEADS[4] = {3, 6, 12, 24};
+constexpr int STEP_CHUNK = 8;     // decode steps between early-exit polls
+
+struct HostTensor {
+  std::vector<float> f;
+  std::vector<int64_t> i;
+  std::vector<int64_t> shape;
+};
+
+struct Lin {
+  __nv_bfloat16* w = nullptr;   // [n, k] bf16 (n padded to a multiple of 32 with zero rows)
+  float* b = nullptr;           // [n] fp32 or nullptr
+  int n = 0, k = 0;
+};
+struct Norm { float* g = nullptr; float* b = nullptr; };
+struct SwinBlock { Norm n1, n2; Lin qkv, proj, fc1, fc2; float* rel_bias = nullptr; };
+struct Merge { Norm norm; Lin red; };
+struct DecLayer { Lin sa_in, sa_out, ca_q, ca_out, l1, l2; Norm n1, n2, n3; };
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+}  // namespace hmocr
+
+using namespace hmocr;
+
+struct hmocr_engine {
+  hmocr_config cfg;
+  int device = 0;
+  int vpad = 0;                       // vocab padded to a multiple of 256
+  std::map<std::string, HostTensor> host;
+  bool finalized = false;
+
+  // device weights (one arena)
+  uint8_t* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
+  float *pe_w = nullptr, *pe_b = nullptr;
+  Norm pe_norm;
+  SwinBlock blocks[12];
+  Merge merges[3];
+  Lin proj;
+  float *emb = nullptr, *pos = nullptr;
+  std::vector<DecLayer> layers;
+  Lin ca_kv;                          // stacked cross-attention K/V projection of all layers [L*2d, d]
+  Lin fc;
+
+  // scratch (grow-only); any reallocation invalidates the captured step graphs
+  std::map<std::string, Buf> ws;
+  uint64_t ws_epoch = 0;
+
+  struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; };
+  std::map<long long, StepGraph> graphs;   // key: rows
+  cudaStream_t cap_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // enc start, enc end, dec end, poll
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  DecodeState* pinned_state = nullptr;   // [2]
+  float last_enc_ms = 0.f, last_dec_ms = 0.f;
+  bool timings_pending = false;
+};
+
+namespace hmocr {
+namespace {
+
+template <class T>
+int ws_get(hmocr_engine* e, const char* name, size_t count, T** out) {
+  Buf& b = e->ws[name];
+  const size_t bytes = count * sizeof(T);
+  if (b.cap < bytes) {
+    if (b.p != nullptr) {
+      HM_CUDA(cudaDeviceSynchronize());
+      HM_CUDA(cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+    }
+    const size_t want = bytes + bytes / 8 + 256;
+    HM_CUDA(cudaMalloc(&b.p, want));
+    b.cap = want;
+    ++e->ws_epoch;
+  }
+  *out = reinterpret_cast<T*>(b.p);
+  return 0;
+}
+
+int arena_alloc(hmocr_engine* e, size_t bytes, void** out) {
+  const size_t off = (e->arena_used + 255) & ~size_t(255);
+  HM_CHECK(off + bytes <= e->arena_cap, "weight arena overflow (%zu + %zu > %zu)", off, bytes, e->arena_cap);
+  *out = e->arena + off;
+  e->arena_used = off + bytes;
+  return 0;
+}
+
+const HostTensor* find(hmocr_engine* e, const std::string& key) {
+  auto it = e->host.find(key);
+  return it == e->host.end() ? nullptr : &it->second;
+}
+
+int need(hmocr_engine* e, const std::string& key, std::vector<int64_t> shape, const HostTensor** out) {
+  const HostTensor* t = find(e, key);
+  HM_CHECK(t != nullptr, "missing state-dict entry '%s'", key.c_str());
+  HM_CHECK(t->shape == shape, "state-dict entry '%s' has the wrong shape", key.c_str());
+  HM_CHECK(!t->f.empty(), "state-dict entry '%s' must be float32", key.c_str());
+  *out = t;
+  return 0;
+}
+
+int upload_f32(hmocr_engine* e, const float* src, size_t n, float** out) {
+  void* p;
+  HM_TRY(arena_alloc(e, n * sizeof(float), &p));
+  HM_CUDA(cudaMemcpy(p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<float*>(p);
+  return 0;
+}
+
+int upload_vec(hmocr_engine* e, const std::string& key, int64_t n, float** out) {
+  const HostTensor* t;
+  HM_TRY(need(e, key, {n}, &t));
+  return upload_f32(e, t->f.data(), (size_t)n, out);
+}
+
+int upload_norm(hmocr_engine* e, const std::string& prefix, int64_t n, Norm* out) {
+  HM_TRY(upload_vec(e, prefix + ".weight", n, &out->g));
+  return upload_vec(e, prefix + ".bias", n, &out->b);
+}
+
+// rows [r0, r0+rows) of a [*, k] fp32 matrix -> bf16 [npad, k] (zero padded), bias likewise
+int upload_lin_rows(hmocr_engine* e, const float* w, const float* b, int rows, int k, Lin* out) {
+  const int npad = (rows + 31) / 32 * 32;
+  std::vector<__nv_bfloat16> tmp((size_t)npad * k, __float2bfloat16(0.f));
+  for (size_t i = 0; i < (size_t)rows * k; ++i) tmp[i] = __float2bfloat16(w[i]);
+  void* p;
+  HM_TRY(arena_alloc(e, tmp.size() * 2, &p));
+  HM_CUDA(cudaMemcpy(p, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+  out->w = reinterpret_cast<__nv_bfloat16*>(p);
+  out->n = npad;
+  out->k = k;
+  out->b = nullptr;
+  if (b != nullptr) {
+    std::vector<float> bt(npad, 0.f);
+    memcpy(bt.data(), b, sizeof(float) * rows);
+    HM_TRY(upload_f32(e, bt.data(), npad, &out->b));
+  }
+  return 0;
+}
+
+int upload_lin(hmocr_engine* e, const std::string& prefix, int n, int k, bool bias, Lin* out) {
+  const HostTensor *w, *b = nullptr;
+  HM_TRY(need(e, prefix + ".weight", {n, k}, &w));
+  if (bias) HM_TRY(need(e, prefix + ".bias", {n}, &b));
+  return upload_lin_rows(e, w->f.data(), b ? b->f.data() : nullptr, n, k, out);
+}
+
+int run_lin(cudaStream_t st, const __nv_bfloat16* a, int lda, int M, const Lin& l, GemmEpilogue epi) {
+  epi.bias = l.b;
+  return gemm_bf16(st, a, lda, M, l.k, l.w, l.n, epi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder schedule            /root/reference/src/model_swin.py:39-46 over swin_t.features
+// ------------------------------------------------------------------------------------------------
+int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, __nv_bfloat16* enc16, cudaStream_t st) {
+  const size_t tok1 = (size_t)B * 24 * 80;
+  float *xa, *xb;
+  __nv_bfloat16 *xn, *qkv, *ctx, *hid;
+  HM_TRY(ws_get(e, "enc.xa", tok1 * 96, &xa));
+  HM_TRY(ws_get(e, "enc.xb", tok1 * 96 / 2, &xb));
+  HM_TRY(ws_get(e, "enc.xn", tok1 * 96, &xn));
+  HM_TRY(ws_get(e, "enc.qkv", tok1 * 288, &qkv));
+  HM_TRY(ws_get(e, "enc.ctx", tok1 * 96, &ctx));
+  HM_TRY(ws_get(e, "enc.hid", tok1 * 384, &hid));
+
+  HM_TRY(patch_embed(st, images, B, e->pe_w, e->pe_b, e->pe_norm.g, e->pe_norm.b, xa));
+  int H = 24, W = 80, C = 96, blk = 0;
+  float* x = xa;
+  float* other = xb;
+  for (int s = 0; s < 4; ++s) {
+    const int rows = B * H * W;
+    for (int j = 0; j < DEPTHS[s]; ++j, ++blk) {
+      const SwinBlock& sb = e->blocks[blk];
+      HM_TRY(layernorm(st, x, rows, C, sb.n1.g, sb.n1.b, xn, nullptr));
+      GemmEpilogue eq;
+      eq.out_bf16 = qkv; eq.ld16 = 3 * C;
+      HM_TRY(run_lin(st, xn, C, rows, sb.qkv, eq));
+      HM_TRY(window_attention(st, qkv, sb.qkv.b, sb.rel_bias, B, H, W, C, HEADS[s], (j & 1) ? 3 : 0, ctx));
+      GemmEpilogue ep;
+      ep.residual = x; ep.ldr = C; ep.out_f32 = x; ep.ld32 = C;
+      HM_TRY(run_lin(st, ctx, C, rows, sb.proj, ep));
+      HM_TRY(layernorm(st, x, rows, C, sb.n2.g, sb.n2.b, xn, nullptr));
+      GemmEpilogue e1;
+      e1.act = 1; e1.out_bf16 = hid; e1.ld16 = 4 * C;
+      HM_TRY(run_lin(st, xn, C, rows, sb.fc1, e1));
+      GemmEpilogue e2;
+      e2.residual = x; e2.ldr = C; e2.out_f32 = x; e2.ld32 = C;
+      HM_TRY(run_lin(st, hid, 4 * C, rows, sb.fc2, e2));
+    }
+    if (s < 3) {
+      const Merge& m = e->merges[s];
+      HM_TRY(patch_merge_ln(st, x, B, H, W, C, m.norm.g, m.norm.b, xn));
+      GemmEpilogue em;
+      em.out_f32 = other; em.ld32 = 2 * C;
+      HM_TRY(run_lin(st, xn, 4 * C, rows / 4, m.red, em));
+      float* t = x; x = other; other = t;
+      // the smaller buffer (xb) can hold every later stage; keep ping-ponging between xa and xb
+      H /= 2; W /= 2; C *= 2;
+    }
+  }
+  const int rows = B * MEM_S;
+  HM_TRY(f32_to_bf16(st, x, (size_t)rows * SWIN_OUT, xn));
+  GemmEpilogue eo;
+  eo.out_f32 = enc32; eo.ld32 = e->cfg.d_model;
+  eo.out_bf16 = enc16; eo.ld16 = e->cfg.d_model;
+  HM_TRY(run_lin(st, xn, SWIN_OUT, rows, e->proj, eo));
+  return 0;
+}
+
+// memory K/V of all layers in one GEMM: memkv[b*S+s, l*2d + {0..d-1: K, d..2d-1: V}]
+int project_memory(hmocr_engine* e, const __nv_bfloat16* enc16, int B, __nv_bfloat16* memkv, cudaStream_t st) {
+  GemmEpilogue ek;
+  ek.out_bf16 = memkv; ek.ld16 = e->ca_kv.n;
+  return run_lin(st, enc16, e->cfg.d_model, B * MEM_S, e->ca_kv, ek);
+}
+
+struct DecBufs {
+  float* x32;
+  __nv_bfloat16 *x16, *qkv, *q, *ctx, *hid;
+  float* logits;
+};
+
+int dec_bufs(hmocr_engine* e, const char* tag, size_t rows, DecBufs* b) {
+  const int d = e->cfg.d_model, ff = e->cfg.dim_feedforward;
+  std::string t(tag);
+  HM_TRY(ws_get(e, (t + ".x32").c_str(), rows * d, &b->x32));
+  HM_TRY(ws_get(e, (t + ".x16").c_str(), rows * d, &b->x16));
+  HM_TRY(ws_get(e, (t + ".qkv").c_str(), rows * 3 * d, &b->qkv));
+  HM_TRY(ws_get(e, (t + ".q").c_str(), rows * d, &b->q));
+  HM_TRY(ws_get(e, (t + ".ctx").c_str(), rows * d, &b->ctx));
+  HM_TRY(ws_get(e, (t + ".hid").c_str(), rows * ff, &b->hid));
+  HM_TRY(ws_get(e, (t + ".logits").c_str(), rows * e->vpad, &b->logits));
+  return 0;
+}
+
+// everything of one decoder layer after the self-attention context is in b.ctx
+int layer_tail(hmocr_engine* e, const DecLayer& L, int l, const DecBufs& b, int rows, const __nv_bfloat16* memkv,
+               const int* mem_row, int T, cudaStream_t st) {
+  const int d = e->cfg.d_model, ff = e->cfg.dim_feedforward, nh = e->cfg.nhead;
+  GemmEpilogue e1;                       // x = LN1(x + out_proj(ctx))
+  e1.residual = b.x32; e1.ldr = d; e1.out_f32 = b.x32; e1.ld32 = d; e1.out_bf16 = b.x16; e1.ld16 = d;
+  e1.ln_gamma = L.n1.g; e1.ln_beta = L.n1.b;
+  HM_TRY(run_lin(st, b.ctx, d, rows, L.sa_out, e1));
+  GemmEpilogue eq;
+  eq.out_bf16 = b.q; eq.ld16 = d;
+  HM_TRY(run_lin(st, b.x16, d, rows, L.ca_q, eq));
+  if (T > 0)
+    HM_TRY(mha_prefill_cross(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, rows / T, T, MEM_S, nh, b.ctx));
+  else
+    HM_TRY(cross_attn_step(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, mem_row, rows, MEM_S, nh, b.ctx));
+  GemmEpilogue e2;                       // x = LN2(x + out_proj(ctx))
+  e2.residual = b.x32; e2.ldr = d; e2.out_f32 = b.x32; e2.ld32 = d; e2.out_bf16 = b.x16; e2.ld16 = d;
+  e2.ln_gamma = L.n2.g; e2.ln_beta = L.n2.b;
+  HM_TRY(run_lin(st, b.ctx, d, rows, L.ca_out, e2));
+  GemmEpilogue ef;
+  ef.act = 2; ef.out_bf16 = b.hid; ef.ld16 = ff;
+  HM_TRY(run_lin(st, b.x16, d, rows, L.l1, ef));
+  GemmEpilogue e3;                       // x = LN3(x + linear2(relu(linear1 x)))
+  e3.residual = b.x32; e3.ldr = d; e3.out_f32 = b.x32; e3.ld32 = d; e3.out_bf16 = b.x16; e3.ld16 = d;
+  e3.ln_gamma = L.n3.g; e3.ln_beta = L.n3.b;
+  HM_TRY(run_lin(st, b.hid, ff, rows, L.l2, e3));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// teacher-forced decoder       /root/reference/src/model_swin.py:72-88
+// ------------------------------------------------------------------------------------------------
+int decoder_forward_impl(hmocr_engine* e, const float* enc32, const int64_t* tgt, int B, int T, float* logits,
+                         cudaStream_t st) {
+  const int d = e->cfg.d_model, nh = e->cfg.nhead;
+  const int rows = B * T;
+  __nv_bfloat16 *enc16, *memkv;
+  HM_TRY(ws_get(e, "tf.enc16", (size_t)B * MEM_S * d, &enc16));
+  HM_TRY(ws_get(e, "tf.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  DecBufs b;
+  HM_TRY(dec_bufs(e, "tf", rows, &b));
+  HM_TRY(f32_to_bf16(st, enc32, (size_t)B * MEM_S * d, enc16));
+  HM_TRY(project_memory(e, enc16, B, memkv, st));
+  HM_TRY(embed_tokens(st, tgt, T, B, T, e->emb, e->pos, d, e->cfg.vocab_size, b.x32, b.x16));
+  for (int l = 0; l < e->cfg.num_layers; ++l) {
+    const DecLayer& L = e->layers[l];
+    GemmEpilogue ei;
+    ei.out_bf16 = b.qkv; ei.ld16 = 3 * d;
+    HM_TRY(run_lin(st, b.x16, d, rows, L.sa_in, ei));
+    HM_TRY(mha_prefill_self(st, b.qkv, B, T, nh, b.ctx));
+    HM_TRY(layer_tail(e, L, l, b, rows, memkv, nullptr, T, st));
+  }
+  GemmEpilogue eo;
+  eo.out_f32 = b.logits; eo.ld32 = e->vpad;
+  HM_TRY(run_lin(st, b.x16, d, rows, e->fc, eo));
+  HM_TRY(copy_logits(st, b.logits, e->vpad, rows, e->cfg.vocab_size, logits));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy generate              /root/reference/src/inference.py:15-25 with a KV cache
+// ------------------------------------------------------------------------------------------------
+struct GenBufs {
+  DecBufs b;
+  __nv_bfloat16 *kcache, *vcache;   // [L][rows][nhead][tmax][32]
+  DecodeState* state;
+  uint8_t* finished;
+  int tmax;
+};
+
+int enqueue_step(hmocr_engine* e, const GenBufs& g, int rows, const __nv_bfloat16* memkv, int64_t* tokens,
+                 float* logprob, int max_len, cudaStream_t st) {
+  const int d = e->cfg.d_model, nh = e->cfg.nhead;
+  const size_t layer_stride = (size_t)rows * nh * g.tmax * 32;
+  for (int l = 0; l < e->cfg.num_layers; ++l) {
+    const DecLayer& L = e->layers[l];
+    GemmEpilogue ei;
+    ei.out_bf16 = g.b.qkv; ei.ld16 = 3 * d;
+    HM_TRY(run_lin(st, g.b.x16, d, rows, L.sa_in, ei));
+    HM_TRY(self_attn_step(st, g.state, g.b.qkv, g.kcache + l * layer_stride, g.vcache + l * layer_stride, rows, nh,
+                          g.tmax, g.b.ctx));
+    HM_TRY(layer_tail(e, L, l, g.b, rows, memkv, nullptr, 0, st));
+  }
+  GemmEpilogue eo;
+  eo.out_f32 = g.b.logits; eo.ld32 = e->vpad;
+  HM_TRY(run_lin(st, g.b.x16, d, rows, e->fc, eo));
+  HM_TRY(greedy_select(st, g.state, g.b.logits, e->vpad, e->cfg.vocab_size, rows, tokens, max_len + 1, logprob,
+                       max_len, e->cfg.eos_id, g.finished, e->emb, e->pos, d, e->cfg.max_seq_len, g.b.x32, g.b.x16));
+  HM_TRY(advance_step(st, g.state));
+  return 0;
+}
+
+int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int beam,
+                              int64_t* tokens, float* logprob, int32_t* steps, float* score, cudaStream_t st) {
+  HM_CHECK(beam == 1, "beam search (beam=%d) is not built yet in this round: only greedy (beam=1)", beam);
+  HM_CHECK(max_len >= 1 && max_len <= e->cfg.max_seq_len,
+           "max_len=%d outside [1, %d] (size of pos_encoder, src/model_swin.py:54)", max_len, e->cfg.max_seq_len);
+  (void)score;
+  const int d = e->cfg.d_model, nh = e->cfg.nhead, L = e->cfg.num_layers;
+  const int rows = B;
+  __nv_bfloat16* memkv;
+  HM_TRY(ws_get(e, "gen.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  GenBufs g;
+  g.tmax = e->cfg.max_seq_len;
+  HM_TRY(dec_bufs(e, "gen", rows, &g.b));
+  const size_t cache_elems = (size_t)L * rows * nh * g.tmax * 32;
+  HM_TRY(ws_get(e, "gen.kcache", cache_elems, &g.kcache));
+  HM_TRY(ws_get(e, "gen.vcache", cache_elems, &g.vcache));
+  HM_TRY(ws_get(e, "gen.state", 1, &g.state));
+  HM_TRY(ws_get(e, "gen.finished", rows, &g.finished));
+  // per-call output pointers are baked into the step graph: stage them in engine-owned buffers
+  int64_t* tok_ws;
+  float* lp_ws;
+  HM_TRY(ws_get(e, "gen.tokens", (size_t)rows * (g.tmax + 1), &tok_ws));
+  HM_TRY(ws_get(e, "gen.logprob", (size_t)rows * g.tmax, &lp_ws));
+
+  HM_TRY(project_memory(e, enc16, B, memkv, st));
+  HM_TRY(init_decode(st, g.state, tok_ws, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, g.finished, lp_ws, max_len));
+  HM_TRY(embed_tokens(st, tok_ws, max_len + 1, rows, 1, e->emb, e->pos, d, e->cfg.vocab_size, g.b.x32, g.b.x16));
+
+  // one decode step captured once per (rows, max_len) and replayed: the step index lives in HBM
+  const long long key = (long long)rows * 1024 + max_len;
+  hmocr_engine::StepGraph& sg = e->graphs[key];
+  if (sg.exec == nullptr || sg.epoch != e->ws_epoch) {
+    if (sg.exec != nullptr) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    HM_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const long launches_before = g_launch_count;
+    int rc = enqueue_step(e, g, rows, memkv, tok_ws, lp_ws, max_len, e->cap_stream);
+    g_launch_count = launches_before;            // captured, not launched
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    HM_CUDA(ce);
+    ce = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    HM_CUDA(ce);
+    sg.epoch = e->ws_epoch;
+  }
+  size_t nodes_per_step = 8 * (size_t)L + 3;
+  int launched_steps = 0, poll_idx = 0;
+  bool done = false;
+  for (int s0 = 0; s0 < max_len && !done; s0 += STEP_CHUNK, ++poll_idx) {
+    const int n = (max_len - s0 < STEP_CHUNK) ? (max_len - s0) : STEP_CHUNK;
+    for (int i = 0; i < n; ++i) {
+      HM_CUDA(cudaGraphLaunch(sg.exec, st));
+      g_launch_count += (long)nodes_per_step;
+    }
+    launched_steps += n;
+    const int slot = poll_idx & 1;
+    HM_CUDA(cudaMemcpyAsync(&e->pinned_state[slot], g.state, sizeof(DecodeState), cudaMemcpyDeviceToHost, st));
+    HM_CUDA(cudaEventRecord(e->poll_ev[slot], st));
+    if (poll_idx >= 1) {                         // look at the chunk before: the GPU never idles
+      const int prev = (poll_idx - 1) & 1;
+      HM_CUDA(cudaEventSynchronize(e->poll_ev[prev]));
+      if (e->pinned_state[prev].steps_executed > 0) done = true;   // every row has emitted eos
+    }
+  }
+  (void)launched_steps;
+  HM_TRY(finalize_decode(st, g.state, tok_ws, max_len + 1, rows, max_len, e->cfg.pad_id, lp_ws, steps));
+  HM_CUDA(cudaMemcpyAsync(tokens, tok_ws, sizeof(int64_t) * rows * (max_len + 1), cudaMemcpyDeviceToDevice, st));
+  if (logprob != nullptr)
+    HM_CUDA(cudaMemcpyAsync(logprob, lp_ws, sizeof(float) * rows * max_len, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int beam, int64_t* tokens, float* logprob,
+                  int32_t* steps, float* score, cudaStream_t st) {
+  float* enc32;
+  __nv_bfloat16* enc16;
+  HM_TRY(ws_get(e, "gen.enc32", (size_t)B * MEM_S * e->cfg.d_model, &enc32));
+  HM_TRY(ws_get(e, "gen.enc16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
+  HM_CUDA(cudaEventRecord(e->ev[0], st));
+  HM_TRY(encode_impl(e, images, B, enc32, enc16, st));
+  HM_CUDA(cudaEventRecord(e->ev[1], st));
+  HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));
+  HM_CUDA(cudaEventRecord(e->ev[2], st));
+  e->timings_pending = true;
+  return 0;
+}
+
+int check_ready(hmocr_engine* e, int B) {
+  HM_CHECK(e != nullptr, "null engine");
+  HM_CHECK(e->finalized, "weights not loaded: call hmocr_load_weight for every entry, then hmocr_finalize_weights");
+  HM_CHECK(B >= 1, "batch must be >= 1 (got %d)", B);
+  HM_CUDA(cudaSetDevice(e->device));
+  return 0;
+}
+
+}  // namespace
+}  // namespace hmocr
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+HM_API const char* hmocr_last_error(void) { return g_err; }
+HM_API const char* hmocr_version(void) { return "hmocr 0.1 (sm_100a, tcgen05/TMA)"; }
+HM_API int64_t hmocr_launch_count(void) { return g_launch_count; }
+
+HM_API int hmocr_create(const hmocr_config* cfg, hmocr_engine** out) {
+  HM_CHECK(cfg != nullptr && out != nullptr, "hmocr_create: null argument");
+  HM_CHECK(cfg->d_model == 256 && cfg->nhead == 8,
+           "this build supports d_model=256, nhead=8 (head_dim 32) as in the reference config; got %d/%d",
+           cfg->d_model, cfg->nhead);
+  HM_CHECK(cfg->dim_feedforward % 64 == 0 && cfg->dim_feedforward > 0, "dim_feedforward must be a multiple of 64");
+  HM_CHECK(cfg->num_layers >= 1 && cfg->num_layers <= 32, "num_layers out of range");
+  HM_CHECK(cfg->max_seq_len >= 2 && cfg->max_seq_len <= 256, "max_seq_len must be in [2,256]");
+  HM_CHECK(cfg->vocab_size >= 4, "vocab_size too small");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  HM_CHECK(ce == cudaSuccess && ndev > 0, "no CUDA device: libhmocr has no CPU fallback (%s)", cudaGetErrorString(ce));
+  HM_TRY(gemm_init());
+  hmocr_engine* e = new hmocr_engine();
+  e->cfg = *cfg;
+  HM_CUDA(cudaGetDevice(&e->device));
+  e->vpad = (cfg->vocab_size + 255) / 256 * 256;
+  e->layers.resize(cfg->num_layers);
+  HM_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) HM_CUDA(cudaEventCreate(&e->ev[i]));
+  for (int i = 0; i < 2; ++i) HM_CUDA(cudaEventCreateWithFlags(&e->poll_ev[i], cudaEventDisableTiming));
+  HM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->pinned_state), 2 * sizeof(DecodeState)));
+  *out = e;
+  return 0;
+}
+
+HM_API void hmocr_destroy(hmocr_engine* e) {
+  if (e == nullptr) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : e->ws)
+    if (kv.second.p) cudaFree(kv.second.p);
+  if (e->arena) cudaFree(e->arena);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (int i = 0; i < 4; ++i)
+    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (e->poll_ev[i]) cudaEventDestroy(e->poll_ev[i]);
+  if (e->pinned_state) cudaFreeHost(e->pinned_state);
+  delete e;
+}
+
+HM_API int hmocr_load_weight(hmocr_engine* e, const char* key, const void* data, const int64_t* shape, int ndim,
+                             int dtype) {
+  HM_CHECK(e != nullptr && key != nullptr && data != nullptr, "hmocr_load_weight: null argument");
+  HM_CHECK(!e->finalized, "weights already finalized");
+  HM_CHECK(dtype == HMOCR_F32 || dtype == HMOCR_I64, "unsupported dtype %d for '%s'", dtype, key);
+  std::string k(key);
+  // the reference registers the Swin trunk twice (encoder.swin.features.* and encoder.features.*
+  // share storage, src/model_swin.py:35); keep one canonical name
+  const std::string alias = "encoder.swin.features.";
+  if (k.compare(0, alias.size(), alias) == 0) k = "encoder.features." + k.substr(alias.size());
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  if (dtype == HMOCR_F32) t.f.assign(static_cast<const float*>(data), static_cast<const float*>(data) + n);
+  else t.i.assign(static_cast<const int64_t*>(data), static_cast<const int64_t*>(data) + n);
+  e->host[k] = std::move(t);
+  return 0;
+}
+
+HM_API int hmocr_finalize_weights(hmocr_engine* e) {
+  HM_CHECK(e != nullptr, "null engine");
+  HM_CHECK(!e->finalized, "weights already finalized");
+  HM_CUDA(cudaSetDevice(e->device));
+  const hmocr_config& c = e->cfg;
+  const int d = c.d_model, ff = c.dim_feedforward, V = c.vocab_size;
+  size_t total = 0;
+  for (auto& kv : e->host) total += kv.second.f.size() * 4 + 1024;
+  e->arena_cap = total + (size_t)e->vpad * d * 4 + (size_t)c.num_layers * 2 * d * (d + 1) * 4 + (64u << 20);
+  HM_CUDA(cudaMalloc(&e->arena, e->arena_cap));
+  e->arena_used = 0;
+
+  const std::string f = "encoder.features.";
+  const HostTensor* t;
+  HM_TRY(need(e, f + "0.0.weight", {96, 1, 4, 4}, &t));
+  HM_TRY(upload_f32(e, t->f.data(), 96 * 16, &e->pe_w));
+  HM_TRY(upload_vec(e, f + "0.0.bias", 96, &e->pe_b));
+  HM_TRY(upload_norm(e, f + "0.2", 96, &e->pe_norm));
+  int C = 96, blk = 0;
+  for (int s = 0; s < 4; ++s) {
+    const int fi = 1 + 2 * s, heads = HEADS[s];
+    for (int j = 0; j < DEPTHS[s]; ++j, ++blk) {
+      const std::string p = f + std::to_string(fi) + "." + std::to_string(j) + ".";
+      SwinBlock& sb = e->blocks[blk];
+      HM_TRY(upload_norm(e, p + "norm1", C, &sb.n1));
+      HM_TRY(upload_norm(e, p + "norm2", C, &sb.n2));
+      HM_TRY(upload_lin(e, p + "attn.qkv", 3 * C, C, true, &sb.qkv));
+      HM_TRY(upload_lin(e, p + "attn.proj", C, C, true, &sb.proj));
+      HM_TRY(upload_lin(e, p + "mlp.0", 4 * C, C, true, &sb.fc1));
+      HM_TRY(upload_lin(e, p + "mlp.3", C, 4 * C, true, &sb.fc2));
+      // relative position bias gathered to [heads,49,49]  (swin_transformer.py:49-56)
+      const HostTensor* tab;
+      HM_TRY(need(e, p + "attn.relative_position_bias_table", {169, heads}, &tab));
+      const HostTensor* idx = find(e, p + "attn.relative_position_index");
+      HM_CHECK(idx != nullptr && idx->i.size() == 2401, "missing/invalid '%sattn.relative_position_index'", p.c_str());
+      std::vector<float> rb((size_t)heads * 2401);
+      for (int q = 0; q < 2401; ++q) {
+        const int64_t r = idx->i[q];
+        HM_CHECK(r >= 0 && r < 169, "relative_position_index out of range");
+        for (int h = 0; h < heads; ++h) rb[(size_t)h * 2401 + q] = tab->f[(size_t)r * heads + h];
+      }
+      HM_TRY(upload_f32(e, rb.data(), rb.size(), &sb.rel_bias));
+    }
+    if (s < 3) {
+      const std::string p = f + std::to_string(fi + 1) + ".";
+      HM_TRY(upload_norm(e, p + "norm", 4 * C, &e->merges[s].norm));
+      HM_TRY(upload_lin(e, p + "reduction", 2 * C, 4 * C, false, &e->merges[s].red));
+      C *= 2;
+    }
+  }
+  HM_TRY(upload_lin(e, "encoder.projection", d, SWIN_OUT, true, &e->proj));
+
+  HM_TRY(need(e, "decoder.embedding.weight", {V, d}, &t));
+  HM_TRY(upload_f32(e, t->f.data(), (size_t)V * d, &e->emb));
+  HM_TRY(need(e, "decoder.pos_encoder.weight", {c.max_seq_len, d}, &t));
+  HM_TRY(upload_f32(e, t->f.data(), (size_t)c.max_seq_len * d, &e->pos));
+  std::vector<float> kvw((size_t)c.num_layers * 2 * d * d), kvb((size_t)c.num_layers * 2 * d);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const std::string p = "decoder.decoder.layers." + std::to_string(l) + ".";
+    DecLayer& L = e->layers[l];
+    const HostTensor *w, *b;
+    HM_TRY(need(e, p + "self_attn.in_proj_weight", {3 * d, d}, &w));
+    HM_TRY(need(e, p + "self_attn.in_proj_bias", {3 * d}, &b));
+    HM_TRY(upload_lin_rows(e, w->f.data(), b->f.data(), 3 * d, d, &L.sa_in));
+    HM_TRY(upload_lin(e, p + "self_attn.out_proj", d, d, true, &L.sa_out));
+    HM_TRY(need(e, p + "multihead_attn.in_proj_weight", {3 * d, d}, &w));
+    HM_TRY(need(e, p + "multihead_attn.in_proj_bias", {3 * d}, &b));
+    HM_TRY(upload_lin_rows(e, w->f.data(), b->f.data(), d, d, &L.ca_q));          // rows [0,d) = Wq
+    memcpy(&kvw[(size_t)l * 2 * d * d], w->f.data() + (size_t)d * d, sizeof(float) * 2 * d * d);   // Wk | Wv
+    memcpy(&kvb[(size_t)l * 2 * d], b->f.data() + d, sizeof(float) * 2 * d);
+    HM_TRY(upload_lin(e, p + "multihead_attn.out_proj", d, d, true, &L.ca_out));
+    HM_TRY(upload_lin(e, p + "linear1", ff, d, true, &L.l1));
+    HM_TRY(upload_lin(e, p + "linear2", d, ff, true, &L.l2));
+    HM_TRY(upload_norm(e, p + "norm1", d, &L.n1));
+    HM_TRY(upload_norm(e, p + "norm2", d, &L.n2));
+    HM_TRY(upload_norm(e, p + "norm3", d, &L.n3));
+  }
+  HM_TRY(upload_lin_rows(e, kvw.data(), kvb.data(), c.num_layers * 2 * d, d, &e->ca_kv));
+  {
+    const HostTensor *w, *b;
+    HM_TRY(need(e, "decoder.fc_out.weight", {V, d}, &w));
+    HM_TRY(need(e, "decoder.fc_out.bias", {V}, &b));
+    std::vector<float> wp((size_t)e->vpad * d, 0.f), bp(e->vpad, 0.f);
+    memcpy(wp.data(), w->f.data(), sizeof(float) * (size_t)V * d);
+    memcpy(bp.data(), b->f.data(), sizeof(float) * V);
+    HM_TRY(upload_lin_rows(e, wp.data(), bp.data(), e->vpad, d, &e->fc));
+  }
+  e->host.clear();
+  e->finalized = true;
+  return 0;
+}
+
+HM_API int hmocr_encode(hmocr_engine* e, const float* images, int B, float* enc_out, void* stream) {
+  HM_TRY(check_ready(e, B));
+  HM_CHECK(images != nullptr && enc_out != nullptr, "hmocr_encode: null buffer");
+  __nv_bfloat16* enc16;
+  HM_TRY(ws_get(e, "enc.out16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
+  return encode_impl(e, images, B, enc_out, enc16, static_cast<cudaStream_t>(stream));
+}
+
+HM_API int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out, const int64_t* tgt, int B, int T,
+                                 float* logits, void* stream) {
+  HM_TRY(check_ready(e, B));
+  HM_CHECK(enc_out != nullptr && tgt != nullptr && logits != nullptr, "hmocr_decoder_forward: null buffer");
+  HM_CHECK(T >= 1 && T <= e->cfg.max_seq_len, "T=%d outside [1,%d] (tgt_mask / pos_encoder size)", T,
+           e->cfg.max_seq_len);
+  return decoder_forward_impl(e, enc_out, tgt, B, T, logits, static_cast<cudaStream_t>(stream));
+}
+
+HM_API int hmocr_generate(hmocr_engine* e, const float* images, int B, int max_len, int beam, int64_t* tokens,
+                          float* logprob, int32_t* steps, float* score, void* stream) {
+  HM_TRY(check_ready(e, B));
+  HM_CHECK(images != nullptr && tokens != nullptr, "hmocr_generate: null buffer");
+  return generate_impl(e, images, B, max_len, beam, tokens, logprob, steps, score, static_cast<cudaStream_t>(stream));
+}
+
+HM_API int hmocr_generate_from_memory(hmocr_engine* e, const float* enc_out, int B, int max_len, int beam,
+                                      int64_t* tokens, float* logprob, int32_t* steps, float* score, void* stream) {
+  HM_TRY(check_ready(e, B));
+  HM_CHECK(enc_out != nullptr && tokens != nullptr, "hmocr_generate_from_memory: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* enc16;
+  HM_TRY(ws_get(e, "gen.enc16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
+  HM_TRY(f32_to_bf16(st, enc_out, (size_t)B * MEM_S * e->cfg.d_model, enc16));
+  HM_CUDA(cudaEventRecord(e->ev[0], st));
+  HM_CUDA(cudaEventRecord(e->ev[1], st));
+  HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));
+  HM_CUDA(cudaEventRecord(e->ev[2], st));
+  e->timings_pending = true;
+  return 0;
+}
+
+HM_API int hmocr_generate_host(hmocr_engine* e, const float* images_host, int B, int max_len, int beam,
+                               int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
+                               void* stream) {
+  HM_TRY(check_ready(e, B));
+  HM_CHECK(images_host != nullptr && tokens_host != nullptr, "hmocr_generate_host: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *img_d, *lp_d, *score_d;
+  int64_t* tok_d;
+  int32_t* steps_d;
+  const size_t img_n = (size_t)B * IMG_H * IMG_W;
+  HM_TRY(ws_get(e, "host.images", img_n, &img_d));
+  HM_TRY(ws_get(e, "host.tokens", (size_t)B * (max_len + 1), &tok_d));
+  HM_TRY(ws_get(e, "host.logprob", (size_t)B * max_len, &lp_d));
+  HM_TRY(ws_get(e, "host.steps", 1, &steps_d));
+  HM_TRY(ws_get(e, "host.score", B, &score_d));
+  HM_CUDA(cudaMemcpyAsync(img_d, images_host, img_n * sizeof(float), cudaMemcpyHostToDevice, st));
+  HM_TRY(generate_impl(e, img_d, B, max_len, beam, tok_d, logprob_host ? lp_d : nullptr, steps_d,
+                       score_host ? score_d : nullptr, st));
+  HM_CUDA(cudaMemcpyAsync(tokens_host, tok_d, sizeof(int64_t) * B * (max_len + 1), cudaMemcpyDeviceToHost, st));
+  if (logprob_host) HM_CUDA(cudaMemcpyAsync(logprob_host, lp_d, sizeof(float) * B * max_len, cudaMemcpyDeviceToHost, st));
+  if (steps_host) HM_CUDA(cudaMemcpyAsync(steps_host, steps_d, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (score_host) HM_CUDA(cudaMemcpyAsync(score_host, score_d, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  HM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+HM_API int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_ms) {
+  HM_CHECK(e != nullptr, "null engine");
+  if (e->timings_pending) {
+    HM_CUDA(cudaEventSynchronize(e->ev[2]));
+    HM_CUDA(cudaEventElapsedTime(&e->last_enc_ms, e->ev[0], e->ev[1]));
+    HM_CUDA(cudaEventElapsedTime(&e->last_dec_ms, e->ev[1], e->ev[2]));
+    e->timings_pending = false;
+  }
+  if (encoder_ms) *encoder_ms = e->last_enc_ms;
+  if (decode_ms) *decode_ms = e->last_dec_ms;
+  return 0;
+}
+
+// ---- kernel-level exports ----------------------------------------------------------------------------
+HM_API int hmocr_gemm_bf16(const void* a, int lda, int M, int K, const void* w, int N, const float* bias, int act,
+                           const float* residual, int ldr, float* out_f32, int ld32, void* out_bf16, int ld16,
+                           const float* ln_gamma, const float* ln_beta, int force_bn, void* stream) {
+  GemmEpilogue epi;
+  epi.bias = bias; epi.act = act; epi.residual = residual; epi.ldr = ldr;
+  epi.out_f32 = out_f32; epi.ld32 = ld32;
+  epi.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); epi.ld16 = ld16;
+  epi.ln_gamma = ln_gamma; epi.ln_beta = ln_beta;
+  return gemm_bf16(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), lda, M, K,
+                   static_cast<const __nv_bfloat16*>(w), N, epi, force_bn);
+}
+
+HM_API int hmocr_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, void* out_bf16,
+                           float* out_f32, void* stream) {
+  return layernorm(static_cast<cudaStream_t>(stream), x, rows, C, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16),
+                   out_f32);
+}
+
+HM_API int hmocr_patch_embed(const float* images, int B, const float* w, const float* b, const float* g,
+                             const float* beta, float* x, void* stream) {
+  return patch_embed(static_cast<cudaStream_t>(stream), images, B, w, b, g, beta, x);
+}
+
+HM_API int hmocr_patch_merge_ln(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
+                                void* out_bf16, void* stream) {
+  return patch_merge_ln(static_cast<cudaStream_t>(stream), x, B, H, W, C, gamma, beta,
+                        static_cast<__nv_bfloat16*>(out_bf16));
+}
+
+HM_API int hmocr_window_attention(const void* qkv, const float* qkv_bias, const float* rel_bias, int B, int H, int W,
+                                  int C, int heads, int shift, void* ctx, void* stream) {
+  return window_attention(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv), qkv_bias,
+                          rel_bias, B, H, W, C, heads, shift, static_cast<__nv_bfloat16*>(ctx));
+}

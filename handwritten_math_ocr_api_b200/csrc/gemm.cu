@@ -1,0 +1,430 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] x W[N,K]^T )      A, W bf16 (K contiguous), fp32 accumulation in TMEM
+//
+// Replaces every nn.Linear on the hot path (torchvision swin_transformer.py:179,215,444,85;
+// /root/reference/src/model_swin.py:45,64,87; torch MultiheadAttention in/out projections,
+// TransformerDecoderLayer.linear1/linear2).
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles
+//              into a STAGES-deep shared-memory ring, completion on "full" mbarriers
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
+//              tcgen05.commit releases the ring slot ("empty") and publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per
+//              thread), fuse bias / GELU / ReLU / fp32 residual / LayerNorm, store fp32 and/or bf16
+// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i overlap the main loop of
+// tile i+1; the producer runs ahead across tile boundaries, so HBM stays busy for the small-K
+// shapes of Swin stage 1/2 where the epilogue dominates.
+#include "gemm.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace hmocr {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NUM_THREADS = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_n_tiles, num_tiles;
+  GemmEpilogue epi;
+};
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (8-row x 128B atoms, 1024B apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);   // start address        bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset  (unused, K-major swizzled)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;          // stride byte offset   bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                  // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4)                 // D format  = F32
+         | (1u << 7)               // A format  = BF16
+         | (1u << 10)              // B format  = BF16
+         | (uint32_t(BN >> 3) << 17)   // N
+         | (uint32_t(BM >> 4) << 24);  // M
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t taddr, int row, bool row_ok,
+                                               int n0) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    const int col = n0 + c * 32;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (e.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 b = __ldg(b4 + q);
+        v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      }
+    }
+    if (e.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (e.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    }
+    if (row_ok) {
+      if (e.residual != nullptr) {
+        const float4* r4 = reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 x = r4[q];
+          v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+        }
+      }
+      if (e.out_f32 != nullptr) {
+        float4* o = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld32 + col);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (e.out_bf16 != nullptr) {
+        uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ld16 + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                            pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+      }
+    }
+  }
+}
+
+// LayerNorm epilogue: the whole output row lives in this thread's TMEM lane (N == BN).
+// Pass 1 writes v = acc + bias (+act) + residual back to TMEM and sums it; pass 2 sums the
+// squared deviations (two-pass variance, as torch does); pass 3 normalises and stores.
+template <int BN>
+__device__ __forceinline__ void epilogue_ln(const GemmEpilogue& e, uint32_t taddr, int row, bool row_ok, int n0) {
+  float sum = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    const int col = n0 + c * 32;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (e.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + col + j);
+    }
+    if (e.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (e.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    }
+    if (row_ok && e.residual != nullptr) {
+      const float4* r4 = reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 x = r4[q];
+        v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { sum += v[j]; r[j] = __float_as_uint(v[j]); }
+    tmem_st32(taddr + c * 32, r);
+  }
+  const float mean = sum * (1.0f / BN);
+  float sq = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { float d = __uint_as_float(r[j]) - mean; sq += d * d; }
+  }
+  const float rstd = rsqrtf(sq * (1.0f / BN) + 1e-5f);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    const int col = n0 + c * 32;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] = (__uint_as_float(r[j]) - mean) * rstd * __ldg(e.ln_gamma + col + j) + __ldg(e.ln_beta + col + j);
+    if (row_ok) {
+      if (e.out_f32 != nullptr) {
+        float4* o = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld32 + col);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (e.out_bf16 != nullptr) {
+        uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ld16 + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                            pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int m0 = (t / p.num_n_tiles) * BM;
+        const int n0 = (t % p.num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          uint8_t* st = smem + s * C::STAGE_BYTES;
+          tma_load_2d(st, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(st + C::A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[a], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t bbase = abase + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, make_smem_desc(abase + k * 32), make_smem_desc(bbase + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(&tfull_bar[a]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;        // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m0 = (t / p.num_n_tiles) * BM;
+      const int n0 = (t % p.num_n_tiles) * BN;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BN;
+      if (p.epi.ln_gamma != nullptr)
+        epilogue_ln<BN>(p.epi, taddr, row, row_ok, n0);
+      else
+        epilogue_plain<BN>(p.epi, taddr, row, row_ok, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+std::mutex g_mu;
+std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+
+int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  alignas(64) CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d", (int)r,
+           ptr, rows, cols, ld, box_rows);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN>
+int launch(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W, int N,
+           const GemmEpilogue& epi) {
+  using C = Cfg<BN>;
+  alignas(64) CUtensorMap tmA, tmB;
+  HM_TRY(get_tensor_map(A, M, K, lda, BM, &tmA));
+  HM_TRY(get_tensor_map(W, N, K, K, BN, &tmB));
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_n_tiles = N / BN;
+  p.num_tiles = ceil_div(M, BM) * p.num_n_tiles;
+  p.epi = epi;
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  HM_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+int gemm_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_encode != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  HM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  HM_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+  int dev = 0;
+  HM_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  HM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  HM_CHECK(prop.major == 10, "libhmocr is built for sm_100a only; device is sm_%d%d (no fallback path)", prop.major,
+           prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  // set once, up front: nothing but launches may happen while a step graph is being captured
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<96>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<192>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+int gemm_bf16(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W, int N,
+              const GemmEpilogue& epi, int force_bn) {
+  HM_TRY(gemm_init());
+  HM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  HM_CHECK(N % 32 == 0, "gemm: N=%d must be a multiple of 32 (pad the weight)", N);
+  HM_CHECK(K % 8 == 0 && lda % 8 == 0, "gemm: K=%d and lda=%d must be multiples of 8", K, lda);
+  HM_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+           "gemm: operands must be 16-byte aligned");
+  HM_CHECK(epi.out_f32 != nullptr || epi.out_bf16 != nullptr, "gemm: no output");
+  HM_CHECK(epi.out_f32 == nullptr || epi.ld32 % 4 == 0, "gemm: ld32 must be a multiple of 4");
+  HM_CHECK(epi.out_bf16 == nullptr || epi.ld16 % 8 == 0, "gemm: ld16 must be a multiple of 8");
+  HM_CHECK(epi.residual == nullptr || epi.ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
+  int bn = force_bn;
+  if (epi.ln_gamma != nullptr) {
+    HM_CHECK(N == 64 || N == 96 || N == 128 || N == 192 || N == 256,
+             "gemm: fused LayerNorm needs N in {64,96,128,192,256}, got %d", N);
+    HM_CHECK(epi.ln_beta != nullptr, "gemm: ln_beta missing");
+    bn = N;
+  }
+  if (bn == 0) {
+    const int cands[5] = {256, 192, 128, 96, 64};
+    const int mt = ceil_div(M, BM);
+    int smallest = 0;
+    for (int i = 0; i < 5; ++i) {
+      if (N % cands[i] != 0) continue;
+      smallest = cands[i];
+      if (bn == 0 && mt * (N / cands[i]) >= g_num_sms) bn = cands[i];
+    }
+    if (bn == 0) bn = smallest;
+    HM_CHECK(bn != 0, "gemm: N=%d is not a multiple of 64 or 96", N);
+  }
+  HM_CHECK(N % bn == 0, "gemm: N=%d not divisible by tile width %d", N, bn);
+  switch (bn) {
+    case 64: return launch<64>(stream, A, lda, M, K, W, N, epi);
+    case 96: return launch<96>(stream, A, lda, M, K, W, N, epi);
+    case 128: return launch<128>(stream, A, lda, M, K, W, N, epi);
+    case 192: return launch<192>(stream, A, lda, M, K, W, N, epi);
+    case 256: return launch<256>(stream, A, lda, M, K, W, N, epi);
+  }
+  HM_CHECK(false, "gemm: unsupported tile width %d", bn);
+  return -2;
+}
+
+}  // namespace hmocr

@@ -1,0 +1,29 @@
+// tcgen05 GEMM with fused epilogues:  C[M,N] = epi( A[M,K] (bf16, K-major) x W[N,K]^T (bf16) )
+#pragma once
+#include "common.cuh"
+
+namespace hmocr {
+
+struct GemmEpilogue {
+  const float* bias = nullptr;        // [N] fp32
+  int act = 0;                        // 0 none, 1 GELU(erf), 2 ReLU
+  const float* residual = nullptr;    // fp32 [M, ldr]; may alias out_f32 (in-place residual add)
+  int ldr = 0;
+  float* out_f32 = nullptr;           // fp32 [M, ld32]
+  int ld32 = 0;
+  __nv_bfloat16* out_bf16 = nullptr;  // bf16 [M, ld16]
+  int ld16 = 0;
+  // LayerNorm over the N axis applied after bias/act/residual; needs N == tile width
+  // (N in {64,96,128,192,256}).  Outputs then hold the normalised rows.
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+};
+
+// A: bf16 [M, K] with row pitch lda (elements); W: bf16 [N, K] contiguous.
+// Requirements: N % 32 == 0 (pad the weight), lda % 8 == 0, K % 8 == 0, 16-byte aligned pointers.
+int gemm_bf16(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W,
+              int N, const GemmEpilogue& epi, int force_bn = 0);
+
+int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
+
+}  // namespace hmocr

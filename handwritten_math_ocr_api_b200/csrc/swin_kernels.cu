@@ -1,0 +1,307 @@
+// Non-GEMM kernels of the Swin-T encoder (sm_100a): patch embedding + LN, LayerNorm,
+// PatchMerging gather + LN, fused shifted-window attention.
+#include "kernels.cuh"
+
+namespace hmocr {
+namespace {
+
+constexpr float LN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (one warp per row, row held in registers, two-pass variance)
+// swin_transformer.py:433,443 (norm1/norm2), :74 (PatchMerging.norm); torch LayerNorm eps 1e-5
+// ------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 12;   // float4 per lane: C <= 1536
+
+struct RowSrc {
+  const float* x;
+  int C;
+  __device__ __forceinline__ const float4* vec(int row, int idx) const {
+    return reinterpret_cast<const float4*>(x + (size_t)row * C) + idx;
+  }
+};
+
+// PatchMerging: output row (b,i,j) = concat of x[b,2i+dr,2j+dc,:] for (dr,dc) in (0,0),(1,0),(0,1),(1,1)
+struct MergeSrc {
+  const float* x;
+  int H, W, Cin;   // input grid and channels; output C = 4*Cin
+  __device__ __forceinline__ const float4* vec(int row, int idx) const {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int j = row % Wo, i = (row / Wo) % Ho, b = row / (Wo * Ho);
+    const int per = Cin >> 2;
+    const int seg = idx / per, within = idx - seg * per;
+    const int r = 2 * i + (seg & 1), c = 2 * j + (seg >> 1);
+    return reinterpret_cast<const float4*>(x + ((size_t)(b * H + r) * W + c) * Cin) + within;
+  }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(256) layernorm_kernel(Src src, int rows, int C, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C >> 2;
+  float4 v[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = *src.vec(row, idx);
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / C + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out16 != nullptr)
+        reinterpret_cast<uint2*>(out16 + (size_t)row * C)[idx] = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      if (out32 != nullptr) reinterpret_cast<float4*>(out32 + (size_t)row * C)[idx] = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Patch embedding: Conv2d(1,96,k4,s4) + NHWC + LayerNorm(96)     swin_transformer.py:556-562
+// one warp per token; lane owns channels lane, lane+32, lane+64
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, int ntok,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          const float* __restrict__ g, const float* __restrict__ beta,
+                                                          float* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float wr[3][16], br[3], gr[3], ber[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int ch = lane + 32 * c;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wr[c][k] = __ldg(w + ch * 16 + k);
+    br[c] = __ldg(bias + ch);
+    gr[c] = __ldg(g + ch);
+    ber[c] = __ldg(beta + ch);
+  }
+  for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < ntok; tok += warps_total) {
+    const int tx = tok % 80, ty = (tok / 80) % 24, b = tok / 1920;
+    const float* base = img + ((size_t)b * 96 + ty * 4) * 320 + tx * 4;
+    float px[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(base + r * 320));
+      px[4 * r] = p.x; px[4 * r + 1] = p.y; px[4 * r + 2] = p.z; px[4 * r + 3] = p.w;
+    }
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float a = br[c];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a = fmaf(px[k], wr[c][k], a);
+      o[c] = a;
+    }
+    const float mean = warp_sum(o[0] + o[1] + o[2]) * (1.0f / 96.0f);
+    const float d0 = o[0] - mean, d1 = o[1] - mean, d2 = o[2] - mean;
+    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.0f / 96.0f) + LN_EPS);
+    float* xo = x + (size_t)tok * 96;
+    xo[lane] = d0 * rstd * gr[0] + ber[0];
+    xo[lane + 32] = d1 * rstd * gr[1] + ber[1];
+    xo[lane + 64] = d2 * rstd * gr[2] + ber[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused shifted-window attention core.                         swin_transformer.py:151-214,219-227
+//
+// One CTA = one 7x7 window of one image x 3 heads.  The cyclic shift, the zero padding, the window
+// partition and their inverses are index arithmetic on the un-shifted, un-padded qkv buffer:
+// rolled position (r,c) reads padded position ((r+sh)%Hp, (c+sw)%Wp); a padded position has
+// q = k = v = qkv.bias (the reference pads with zeros AFTER norm1, so its Linear output is the
+// bias); outputs of padded positions are never written (the reference crops them).
+// Thread = (head, query row): q in registers, K/V of the window in shared memory (fp32),
+// scores + relative-position bias + (-100) region mask, softmax and P.V all in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int WS = 7, WN = 49, HD = 32, HC = 3;
+
+struct WinSmem {
+  float k[HC][WN][HD];
+  float v[HC][WN][HD];
+  float bias[HC][WN][WN];
+  int tok[WN];      // token row in the qkv buffer, -1 if padded
+  int region[WN];
+};
+
+__global__ void __launch_bounds__(HC * 64) window_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                              const float* __restrict__ qkv_bias,
+                                                              const float* __restrict__ rel_bias, int H, int W, int C,
+                                                              int sh, int sw, int Hp, int Wp,
+                                                              __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  WinSmem& s = *reinterpret_cast<WinSmem*>(smem_raw);
+  const int nww = Wp / WS;
+  const int win = blockIdx.x, b = blockIdx.y, h0 = blockIdx.z * HC;
+  const int wr = win / nww, wc = win % nww;
+  const int tid = threadIdx.x;
+
+  if (tid < WN) {
+    const int r = wr * WS + tid / WS, c = wc * WS + tid % WS;      // rolled, padded coordinates
+    const int pr = (r + sh) % Hp, pc = (c + sw) % Wp;              // padded coordinates before the roll
+    s.tok[tid] = (pr < H && pc < W) ? (b * H + pr) * W + pc : -1;
+    int reg = 0;
+    if (sh + sw > 0) {
+      // slices (0,-7),(-7,-s),(-s,None) written in order; s == 0 makes the last one cover everything
+      const int hb = (sh == 0) ? 2 : ((r >= Hp - WS) + (r >= Hp - sh));
+      const int wb = (sw == 0) ? 2 : ((c >= Wp - WS) + (c >= Wp - sw));
+      reg = hb * 3 + wb;
+    }
+    s.region[tid] = reg;
+  }
+  // relative position bias of these 3 heads -> smem (coalesced)
+  for (int i = tid; i < HC * WN * WN; i += blockDim.x) (&s.bias[0][0][0])[i] = __ldg(rel_bias + (size_t)h0 * WN * WN + i);
+  __syncthreads();
+  // K and V rows of the window: 16-byte chunks of 8 bf16
+  for (int i = tid; i < HC * WN * 4 * 2; i += blockDim.x) {
+    const int chunk = i & 3, kv = (i >> 2) & 1, p = (i >> 3) % WN, h = (i >> 3) / WN;
+    const int col = (1 + kv) * C + (h0 + h) * HD + chunk * 8;
+    float* dst = (kv ? &s.v[h][p][0] : &s.k[h][p][0]) + chunk * 8;
+    const int tok = s.tok[p];
+    if (tok >= 0) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + col));
+      float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      dst[0] = a.x; dst[1] = a.y; dst[2] = bb.x; dst[3] = bb.y; dst[4] = cc.x; dst[5] = cc.y; dst[6] = d.x; dst[7] = d.y;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[e] = __ldg(qkv_bias + col + e);
+    }
+  }
+  __syncthreads();
+
+  const int h = tid >> 6, i = tid & 63;
+  if (i >= WN) return;
+  const int tok = s.tok[i];
+  if (tok < 0) return;                       // padded query: its output is cropped by the reference
+  const float scale = 0.17677669529663687f;  // 32^-0.5, applied to q (swin_transformer.py:188)
+  float q[HD];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + (h0 + h) * HD);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const uint4 u = __ldg(qp + c4);
+      float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      q[8 * c4 + 0] = a.x * scale; q[8 * c4 + 1] = a.y * scale; q[8 * c4 + 2] = bb.x * scale; q[8 * c4 + 3] = bb.y * scale;
+      q[8 * c4 + 4] = cc.x * scale; q[8 * c4 + 5] = cc.y * scale; q[8 * c4 + 6] = d.x * scale; q[8 * c4 + 7] = d.y * scale;
+    }
+  }
+  const int my_region = s.region[i];
+  const bool masked = (sh + sw) > 0;
+  float sc[WN];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < WN; ++j) {
+    const float4* kp = reinterpret_cast<const float4*>(&s.k[h][j][0]);
+    float a = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 kk = kp[d4];
+      a = fmaf(q[4 * d4], kk.x, a); a = fmaf(q[4 * d4 + 1], kk.y, a);
+      a = fmaf(q[4 * d4 + 2], kk.z, a); a = fmaf(q[4 * d4 + 3], kk.w, a);
+    }
+    a += s.bias[h][i][j];
+    if (masked && s.region[j] != my_region) a += -100.0f;
+    sc[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  float denom = 0.f;
+  float acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < WN; ++j) {
+    const float p = __expf(sc[j] - mx);
+    denom += p;
+    const float4* vp = reinterpret_cast<const float4*>(&s.v[h][j][0]);
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 vv = vp[d4];
+      acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
+      acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
+    }
+  }
+  const float inv = 1.0f / denom;
+  uint4* op = reinterpret_cast<uint4*>(ctx + (size_t)tok * C + (h0 + h) * HD);
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4)
+    op[c4] = make_uint4(pack_bf16(acc[8 * c4] * inv, acc[8 * c4 + 1] * inv), pack_bf16(acc[8 * c4 + 2] * inv, acc[8 * c4 + 3] * inv),
+                        pack_bf16(acc[8 * c4 + 4] * inv, acc[8 * c4 + 5] * inv), pack_bf16(acc[8 * c4 + 6] * inv, acc[8 * c4 + 7] * inv));
+}
+
+}  // namespace
+
+int layernorm(cudaStream_t st, const float* x, int rows, int C, const float* gamma, const float* beta,
+              __nv_bfloat16* out16, float* out32) {
+  HM_CHECK(C % 4 == 0 && C <= LN_MAXV * 128, "layernorm: C=%d unsupported (multiple of 4, <= %d)", C, LN_MAXV * 128);
+  HM_CHECK(rows > 0, "layernorm: empty input");
+  RowSrc src{x, C};
+  layernorm_kernel<RowSrc><<<ceil_div(rows, 8), 256, 0, st>>>(src, rows, C, gamma, beta, out16, out32);
+  HM_LAUNCHED();
+  return 0;
+}
+
+int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin, const float* gamma,
+                   const float* beta, __nv_bfloat16* out16) {
+  HM_CHECK(H % 2 == 0 && W % 2 == 0, "patch_merge: odd grid %dx%d (the reference pads; never hit at 96x320)", H, W);
+  HM_CHECK(Cin % 4 == 0 && 4 * Cin <= LN_MAXV * 128, "patch_merge: C=%d unsupported", Cin);
+  const int rows = B * (H / 2) * (W / 2);
+  MergeSrc src{x, H, W, Cin};
+  layernorm_kernel<MergeSrc><<<ceil_div(rows, 8), 256, 0, st>>>(src, rows, 4 * Cin, gamma, beta, out16, nullptr);
+  HM_LAUNCHED();
+  return 0;
+}
+
+int patch_embed(cudaStream_t st, const float* images, int B, const float* w, const float* b, const float* g,
+                const float* beta, float* x) {
+  const int ntok = B * 24 * 80;
+  int blocks = ceil_div(ntok, 8 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  patch_embed_kernel<<<blocks, 256, 0, st>>>(images, ntok, w, b, g, beta, x);
+  HM_LAUNCHED();
+  return 0;
+}
+
+int window_attention(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
+                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx) {
+  HM_CHECK(C == heads * HD, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
+  HM_CHECK(heads % HC == 0, "window_attention: heads=%d must be a multiple of %d", heads, HC);
+  const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;
+  const int sh = (Hp > WS) ? shift : 0, sw = (Wp > WS) ? shift : 0;   // swin_transformer.py:158-163
+  static bool attr = false;
+  if (!attr) {
+    HM_CUDA(cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WinSmem)));
+    attr = true;
+  }
+  dim3 grid((Hp / WS) * (Wp / WS), B, heads / HC);
+  window_attn_kernel<<<grid, HC * 64, sizeof(WinSmem), st>>>(qkv, qkv_bias, rel_bias, H, W, C, sh, sw, Hp, Wp, ctx);
+  HM_LAUNCHED();
+  return 0;
+}
+
+}  // namespace hmocr

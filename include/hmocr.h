@@ -1,0 +1,135 @@
+/*
+ * libhmocr - C ABI of the B200-native image-to-LaTeX engine (sm_100a only, no CPU fallback).
+ *
+ * The reference (PTD504/handwritten-math-ocr-api) is pure Python and has no FFI; the boundary it
+ * offers for this path is the nn.Module surface of `FormulaRecognitionModel`
+ * (/root/reference/src/model_swin.py:91-101) and the three greedy drivers built on it.  Each entry
+ * point below names the reference interface it replaces; the Python mirror that binds them with
+ * ctypes is `handwritten_math_ocr_api_b200/`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; the message is available
+ *     from hmocr_last_error() (thread local).  Nothing falls back to another implementation.
+ *   - pointers named *_dev are CUDA device pointers owned by the caller (torch tensors on the
+ *     Python side); *_host are host pointers.  `stream` is a cudaStream_t passed as void*.
+ *     All work is enqueued on that stream; only the *_host entry points synchronise.
+ *   - the engine owns its weights and scratch buffers (allocated at load / first use).
+ *   - one engine = one CUDA device (current device at hmocr_create); not thread-safe per handle.
+ */
+#ifndef HMOCR_H_
+#define HMOCR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hmocr_engine hmocr_engine;
+
+/* Hyper-parameters read from the reference's `config` singleton
+ * (/root/reference/src/config.py:16-47, /root/reference/app/src/config.py:22-57). */
+typedef struct hmocr_config {
+  int32_t vocab_size;      /* len(vocab); 5075 in the reference's MLflow run                   */
+  int32_t d_model;         /* config.d_model          = 256                                    */
+  int32_t nhead;           /* config.nhead            = 8   (head_dim must be 32)              */
+  int32_t dim_feedforward; /* config.dim_feedforward  = 512                                    */
+  int32_t num_layers;      /* config.swin_num_decoder_layers / num_decoder_layers = 8          */
+  int32_t max_seq_len;     /* config.max_seq_len      = 150 (size of pos_encoder / tgt_mask)   */
+  int32_t sos_id, eos_id, pad_id; /* vocab['<sos>'], vocab['<eos>'], vocab['<pad>'] = 1, 2, 0  */
+} hmocr_config;
+
+enum { HMOCR_F32 = 0, HMOCR_I64 = 1 };
+
+const char* hmocr_last_error(void);
+const char* hmocr_version(void);
+/* kernels launched by this library on the calling thread since load (bench.py "gpu_launches") */
+int64_t hmocr_launch_count(void);
+
+/* FormulaRecognitionModel(vocab_size)            /root/reference/src/model_swin.py:91-95 */
+int hmocr_create(const hmocr_config* cfg, hmocr_engine** out);
+void hmocr_destroy(hmocr_engine* e);
+
+/* model.load_state_dict(sd): one call per state-dict entry, reference key names and shapes
+ * (/root/reference/src/predict.py:28-29; layout in SURVEY.md section 8b).  `data_host` is fp32 or int64
+ * host memory; the engine converts / repacks and uploads.  Unknown or unused keys
+ * (encoder.swin.norm.*, encoder.swin.head.*, decoder.tgt_mask, the encoder.swin.features.*
+ * aliases) are accepted and ignored.  hmocr_finalize_weights fails if a needed entry is missing. */
+int hmocr_load_weight(hmocr_engine* e, const char* key, const void* data_host, const int64_t* shape, int ndim,
+                      int dtype);
+int hmocr_finalize_weights(hmocr_engine* e);
+
+/* model.encoder(images)                          /root/reference/src/model_swin.py:39-46
+ * images_dev f32 [B,1,96,320] -> enc_out_dev f32 [B,30,d_model] */
+int hmocr_encode(hmocr_engine* e, const float* images_dev, int batch, float* enc_out_dev, void* stream);
+
+/* model.decoder(encoder_out, tgt)                /root/reference/src/model_swin.py:72-88
+ * enc_out_dev f32 [B,30,d], tgt_dev int64 [B,T] -> logits_dev f32 [B,T,V] (all T positions) */
+int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out_dev, const int64_t* tgt_dev, int batch, int T,
+                          float* logits_dev, void* stream);
+
+/* The greedy loops of /root/reference/src/inference.py:15-25, src/predict.py:56-65 and
+ * app/src/im2latex.py:20-45 as ONE call: encoder once, KV-cached decode, argmax / beam top-k and
+ * the winner's log-softmax on device.
+ *   tokens_dev   int64 [B, 1+max_len]  column 0 = sos; columns past *steps are pad
+ *   logprob_dev  f32   [B, max_len]    log_softmax(logits)[token] per emitted position (may be NULL)
+ *   steps_dev    int32 [1]             number of decode steps executed = ys.shape[1]-1 of the
+ *                                      reference (stops when every row has emitted eos)
+ * beam == 1: greedy, finished rows keep decoding exactly as the reference does.
+ * beam  > 1: beam search as defined in DESIGN.md (the reference has none); tokens are the best
+ *            hypothesis per image, score_dev f32 [B] its summed log-probability (may be NULL). */
+int hmocr_generate(hmocr_engine* e, const float* images_dev, int batch, int max_len, int beam, int64_t* tokens_dev,
+                   float* logprob_dev, int32_t* steps_dev, float* score_dev, void* stream);
+
+/* Same, starting from encoder output already in HBM (src/inference.py:13 split from :15-25). */
+int hmocr_generate_from_memory(hmocr_engine* e, const float* enc_out_dev, int batch, int max_len, int beam,
+                               int64_t* tokens_dev, float* logprob_dev, int32_t* steps_dev, float* score_dev,
+                               void* stream);
+
+/* End-to-end form with HOST buffers (what `predict(images, model, vocab, idx2char, device)` does
+ * around the model: images.to(device) ... ids back on the host): pinned or pageable host memory
+ * in, host memory out, H2D and D2H inside, synchronises before returning. */
+int hmocr_generate_host(hmocr_engine* e, const float* images_host, int batch, int max_len, int beam,
+                        int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
+                        void* stream);
+
+/* Phase timings of the last hmocr_generate* call on this engine, measured with CUDA events on
+ * the caller's stream (valid after the stream has been synchronised): encoder ms, decode ms. */
+int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_ms);
+
+/* ---- individual kernels, exported for the unit tests ------------------------------------- */
+
+/* nn.Linear (+ fused epilogue): out = LN?( act(A W^T + bias) + residual )
+ * A bf16 [M,K] pitch lda, W bf16 [N,K]; act 0 none / 1 GELU(erf) / 2 ReLU; any of bias, residual,
+ * out_f32, out_bf16, ln_gamma/ln_beta may be NULL.  force_bn 0 = automatic tile width. */
+int hmocr_gemm_bf16(const void* a_dev, int lda, int M, int K, const void* w_dev, int N, const float* bias_dev,
+                    int act, const float* residual_dev, int ldr, float* out_f32_dev, int ld32, void* out_bf16_dev,
+                    int ld16, const float* ln_gamma_dev, const float* ln_beta_dev, int force_bn, void* stream);
+
+/* nn.LayerNorm over the last axis: x f32 [rows, C] -> bf16 and/or f32 */
+int hmocr_layernorm(const float* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
+                    void* out_bf16_dev, float* out_f32_dev, void* stream);
+
+/* features[0]: Conv2d(1,96,4,4) + Permute + LayerNorm(96)   (swin_transformer.py:556-562)
+ * images f32 [B,1,96,320] -> x f32 [B,24,80,96] */
+int hmocr_patch_embed(const float* images_dev, int batch, const float* conv_w_dev, const float* conv_b_dev,
+                      const float* ln_g_dev, const float* ln_b_dev, float* x_dev, void* stream);
+
+/* PatchMerging gather + LayerNorm(4C)            (swin_transformer.py:35-43, 84)
+ * x f32 [B,H,W,C] -> bf16 [B,H/2,W/2,4C] (ready for the bias-free reduction GEMM) */
+int hmocr_patch_merge_ln(const float* x_dev, int batch, int H, int W, int C, const float* gamma_dev,
+                         const float* beta_dev, void* out_bf16_dev, void* stream);
+
+/* shifted_window_attention core (swin_transformer.py:151-214, 219-227) on a qkv buffer computed
+ * for the real (un-padded, un-shifted) tokens:
+ *   qkv bf16 [B*H*W, 3C] (bias included), qkv_bias f32 [3C] (value of padded tokens),
+ *   rel_bias f32 [heads,49,49] (table gathered by relative_position_index), shift 0 or 3
+ *   -> ctx bf16 [B*H*W, C] in original token order (input of attn.proj) */
+int hmocr_window_attention(const void* qkv_dev, const float* qkv_bias_dev, const float* rel_bias_dev, int batch,
+                           int H, int W, int C, int heads, int shift, void* ctx_bf16_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMOCR_H_ */

@@ -1,0 +1,204 @@
+"""GPU: each hand-written kernel against plain torch fp32 / the oracle on identical tensors."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gpu_utils import P, S, gemm, gemm_ref  # noqa: E402
+
+
+def _lib():
+    from handwritten_math_ocr_api_b200 import _lib as L
+    return L.load(), L
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale)
+
+
+# every (M, K, N) class on the hot path, shrunk in M to B=2 images, plus tails
+GEMM_SHAPES = [
+    (3840, 96, 288), (3840, 96, 96), (3840, 96, 384), (3840, 384, 96),          # stage 1
+    (960, 384, 192), (960, 192, 576), (960, 192, 192), (960, 192, 768), (960, 768, 192),   # merge 1, stage 2
+    (240, 768, 384), (240, 384, 1152), (240, 384, 384), (240, 384, 1536), (240, 1536, 384),  # merge 2, stage 3
+    (60, 1536, 768), (60, 768, 2304), (60, 768, 768), (60, 768, 3072), (60, 3072, 768),   # merge 3, stage 4
+    (60, 768, 256),                                                              # projection
+    (256, 256, 768), (256, 256, 256), (256, 256, 512), (256, 512, 256), (256, 256, 5120),  # decoder step B=256
+    (1, 256, 768), (7, 256, 5120), (129, 96, 96), (300, 256, 4096),             # ragged M
+    (20000, 96, 288), (19000, 384, 96),                                          # many tiles per CTA (persistence)
+]
+
+
+@pytest.mark.parametrize("M,K,N", GEMM_SHAPES)
+def test_gemm_plain(M, K, N):
+    a = _rand(M, K, seed=1).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
+    o32, o16 = gemm(a, w, out_bf16=True)
+    ref = gemm_ref(a, w)
+    err = (o32 - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err      # fp32 accumulation-order noise only
+    assert (o16.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("bn", [64, 96, 128, 192, 256])
+def test_gemm_every_tile_width(bn):
+    M, K, N = 1000, 320, bn * 3
+    a = _rand(M, K, seed=3).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=4).bfloat16()
+    o32, _ = gemm(a, w, force_bn=bn)
+    assert (o32 - gemm_ref(a, w)).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_bias_act_residual(act):
+    M, K, N = 777, 384, 192
+    a = _rand(M, K, seed=5).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=6).bfloat16()
+    bias, res = _rand(N, seed=7), _rand(M, N, seed=8)
+    o32, o16 = gemm(a, w, bias=bias, act=act, residual=res, out_bf16=True)
+    ref = gemm_ref(a, w, bias, act, res)
+    assert (o32 - ref).abs().max().item() < 3e-3
+    assert (o16.float() - ref).abs().max().item() < 5e-2
+
+
+def test_gemm_residual_in_place():
+    lib, L = _lib()
+    M, K, N = 500, 96, 96
+    a = _rand(M, K, seed=9).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=10).bfloat16()
+    bias = _rand(N, seed=11)
+    x = _rand(M, N, seed=12)
+    ref = gemm_ref(a, w, bias, 0, x.clone())
+    L.check(lib.hmocr_gemm_bf16(P(a), K, M, K, P(w), N, P(bias), 0, P(x), N, P(x), N, None, 0, None, None, 0, S()), "gemm")
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 512), (96, 96), (192, 768)])
+def test_gemm_fused_layernorm(N, K):
+    M = 300
+    a = _rand(M, K, seed=13).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=14).bfloat16()
+    bias, res = _rand(N, seed=15), _rand(M, N, seed=16)
+    g, b = 1 + 0.2 * _rand(N, seed=17), 0.1 * _rand(N, seed=18)
+    o32, o16 = gemm(a, w, bias=bias, residual=res, ln=(g, b), out_bf16=True)
+    ref = gemm_ref(a, w, bias, 0, res, (g, b))
+    assert (o32 - ref).abs().max().item() < 3e-3
+    assert (o16.float() - ref).abs().max().item() < 5e-2
+
+
+def test_gemm_rejects_bad_shapes():
+    lib, L = _lib()
+    a = _rand(8, 64).bfloat16()
+    w = _rand(40, 64).bfloat16()
+    out = torch.empty(8, 40, device="cuda")
+    rc = lib.hmocr_gemm_bf16(P(a), 64, 8, 64, P(w), 40, None, 0, None, 0, P(out), 40, None, 0, None, None, 0, S())
+    assert rc != 0 and b"multiple of 32" in lib.hmocr_last_error()
+
+
+@pytest.mark.parametrize("C_", [96, 192, 384, 768, 1536, 256])
+def test_layernorm(C_):
+    lib, L = _lib()
+    rows = 1000
+    x = _rand(rows, C_, seed=20) * 3 + 0.5
+    g, b = 1 + 0.2 * _rand(C_, seed=21), 0.1 * _rand(C_, seed=22)
+    o16 = torch.empty(rows, C_, dtype=torch.bfloat16, device="cuda")
+    o32 = torch.empty(rows, C_, dtype=torch.float32, device="cuda")
+    L.check(lib.hmocr_layernorm(P(x), rows, C_, P(g), P(b), P(o16), P(o32), S()), "layernorm")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (C_,), g, b, 1e-5)
+    assert (o32 - ref).abs().max().item() < 2e-5
+    assert (o16.float() - ref).abs().max().item() < 4e-2
+
+
+def test_patch_embed_against_oracle(sd):
+    from oracle import ref_model as R
+    from oracle.synth import synth_images
+    lib, L = _lib()
+    imgs = synth_images(3).cuda()
+    dsd = {k: v.cuda() for k, v in sd.items() if k.startswith("encoder.features.0.")}
+    ref = R.patch_embed(imgs, dsd, "encoder.features.")
+    x = torch.empty(3, 24, 80, 96, device="cuda")
+    L.check(lib.hmocr_patch_embed(P(imgs), 3, P(dsd["encoder.features.0.0.weight"]), P(dsd["encoder.features.0.0.bias"]),
+                                  P(dsd["encoder.features.0.2.weight"]), P(dsd["encoder.features.0.2.bias"]), P(x), S()),
+            "patch_embed")
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("H,W,Cin", [(24, 80, 96), (12, 40, 192), (6, 20, 384)])
+def test_patch_merge_ln(H, W, Cin):
+    lib, L = _lib()
+    B = 2
+    x = _rand(B, H, W, Cin, seed=30)
+    g, b = 1 + 0.2 * _rand(4 * Cin, seed=31), 0.1 * _rand(4 * Cin, seed=32)
+    out = torch.empty(B, H // 2, W // 2, 4 * Cin, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.hmocr_patch_merge_ln(P(x), B, H, W, Cin, P(g), P(b), P(out), S()), "patch_merge_ln")
+    torch.cuda.synchronize()
+    cat = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    ref = torch.nn.functional.layer_norm(cat, (4 * Cin,), g, b, 1e-5)
+    assert (out.float() - ref).abs().max().item() < 4e-2
+
+
+@pytest.mark.parametrize("stage,shift", [(0, 0), (0, 3), (1, 0), (1, 3), (2, 0), (2, 3), (3, 0), (3, 3)])
+def test_window_attention_against_oracle(stage, shift):
+    """All four stage geometries incl. the suppressed H-shift (stage 3/4) and the 7x14 padded stage 4."""
+    from oracle import ref_model as R
+    from oracle.arch import stage_dims
+    lib, L = _lib()
+    H, W, C_, heads = stage_dims()[stage]
+    B = 2
+    xn = _rand(B, H, W, C_, seed=40 + stage)
+    bp = "b."
+    dsd = {
+        bp + "attn.qkv.weight": _rand(3 * C_, C_, scale=C_ ** -0.5, seed=50),
+        bp + "attn.qkv.bias": 0.3 * _rand(3 * C_, seed=51),
+        bp + "attn.relative_position_bias_table": _rand(169, heads, seed=52),
+        bp + "attn.proj.weight": torch.eye(C_, device="cuda"),
+        bp + "attn.proj.bias": torch.zeros(C_, device="cuda"),
+    }
+    from oracle.synth import relative_position_index
+    idx = torch.from_numpy(relative_position_index()).cuda()
+    dsd[bp + "attn.relative_position_index"] = idx
+    # feed both sides the SAME bf16-rounded qkv so only the attention core is compared
+    qkv = torch.nn.functional.linear(xn, dsd[bp + "attn.qkv.weight"], dsd[bp + "attn.qkv.bias"]).bfloat16()
+    rel = dsd[bp + "attn.relative_position_bias_table"][idx].reshape(49, 49, heads).permute(2, 0, 1).contiguous()
+    ctx = torch.zeros(B * H * W, C_, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.hmocr_window_attention(P(qkv), P(dsd[bp + "attn.qkv.bias"]), P(rel), B, H, W, C_, heads, shift, P(ctx), S()),
+            "window_attention")
+    torch.cuda.synchronize()
+    # oracle with a qkv Linear that reproduces the rounded qkv: run it on an identity-embedded input
+    # instead: recompute from the rounded tensor by monkey-patching the linear through a hook
+    ref = _oracle_attention_from_qkv(qkv.float().reshape(B, H, W, 3 * C_), dsd, bp, heads, shift)
+    err = (ctx.float().reshape(B, H, W, C_) - ref).abs().max().item()
+    assert err < 3e-2, err
+
+
+def _oracle_attention_from_qkv(qkv, dsd, bp, heads, shift):
+    """oracle.ref_model.window_attention with the qkv Linear factored out (padded rows = bias)."""
+    from oracle import ref_model as R
+    B, H, W, C3 = qkv.shape
+    C_ = C3 // 3
+    hd = C_ // heads
+    Hp, Wp, sh, sw, src, valid, region = R.window_geometry(H, W, shift)
+    nW, N = src.shape
+    src, valid, region = src.cuda(), valid.cuda(), region.cuda()
+    tok = qkv.reshape(B, H * W, C3)[:, src.reshape(-1), :]
+    bias_row = dsd[bp + "attn.qkv.bias"].reshape(1, 1, C3)
+    tok = torch.where(valid.reshape(1, -1, 1), tok, bias_row.expand_as(tok)).reshape(B * nW, N, 3, heads, hd)
+    q, k, v = tok.permute(2, 0, 3, 1, 4)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    table, index = dsd[bp + "attn.relative_position_bias_table"], dsd[bp + "attn.relative_position_index"]
+    attn = attn + table[index].reshape(N, N, heads).permute(2, 0, 1).unsqueeze(0)
+    if sh + sw > 0:
+        diff = region.unsqueeze(1) != region.unsqueeze(2)
+        mask = torch.where(diff, -100.0, 0.0).to(attn.dtype)
+        attn = (attn.reshape(B, nW, heads, N, N) + mask[None, :, None]).reshape(B * nW, heads, N, N)
+    ctx = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B, nW * N, C_)
+    res = qkv.new_zeros(B, H * W, C_)
+    vf = valid.reshape(-1)
+    res[:, src.reshape(-1)[vf], :] = ctx[:, vf, :]
+    return res.reshape(B, H, W, C_)
