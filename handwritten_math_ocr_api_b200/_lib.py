@@ -27,6 +27,7 @@ SIGNATURES = {
     "hmocr_destroy": (None, [_p]),
     "hmocr_load_weight": (_i, [_p, C.c_char_p, _p, _i64p, _i, _i]),
     "hmocr_finalize_weights": (_i, [_p]),
+    "hmocr_set_option": (_i, [_p, C.c_char_p, _i]),
     "hmocr_encode": (_i, [_p, _p, _i, _p, _p]),
     "hmocr_decoder_forward": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "hmocr_generate": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),

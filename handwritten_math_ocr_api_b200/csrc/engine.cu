@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "decode_persistent.cuh"
 #include "gemm.cuh"
 #include "hmocr.h"
 #include "kernels.cuh"
@@ -77,6 +78,12 @@ struct hmocr_engine {
   std::vector<DecLayer> layers;
   Lin ca_kv;                          // stacked cross-attention K/V projection of all layers [L*2d, d]
   Lin fc;
+  // packed operands of the persistent cluster decode kernel (decode_persistent.cuh)
+  uint8_t *dp_wblob = nullptr, *dp_fcblob = nullptr;
+  float *dp_fparams = nullptr, *dp_fcbias = nullptr;
+  int dp_fc_chunks = 0;
+  int decode_impl = 0;                // 0 = persistent cluster kernel, 1 = per-kernel step graph
+  int steps_per_launch = 16;
 
   // scratch (grow-only); any reallocation invalidates the captured step graphs
   std::map<std::string, Buf> ws;
@@ -364,12 +371,16 @@ int enqueue_step(hmocr_engine* e, const GenBufs& g, int rows, const __nv_bfloat1
   return 0;
 }
 
+int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int64_t* tokens,
+                        float* logprob, int32_t* steps, cudaStream_t st);
+
 int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int beam,
                               int64_t* tokens, float* logprob, int32_t* steps, float* score, cudaStream_t st) {
   HM_CHECK(beam == 1, "beam search (beam=%d) is not built yet in this round: only greedy (beam=1)", beam);
   HM_CHECK(max_len >= 1 && max_len <= e->cfg.max_seq_len,
            "max_len=%d outside [1, %d] (size of pos_encoder, src/model_swin.py:54)", max_len, e->cfg.max_seq_len);
   (void)score;
+  if (e->decode_impl == 0) return generate_persistent(e, enc16, B, max_len, tokens, logprob, steps, st);
   const int d = e->cfg.d_model, nh = e->cfg.nhead, L = e->cfg.num_layers;
   const int rows = B;
   __nv_bfloat16* memkv;
@@ -434,6 +445,143 @@ int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B
   HM_CUDA(cudaMemcpyAsync(tokens, tok_ws, sizeof(int64_t) * rows * (max_len + 1), cudaMemcpyDeviceToDevice, st));
   if (logprob != nullptr)
     HM_CUDA(cudaMemcpyAsync(logprob, lp_ws, sizeof(float) * rows * max_len, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// operand packing for decode_persistent.cu (host side, once at load)
+// ------------------------------------------------------------------------------------------------
+void pack_rows(std::vector<__nv_bfloat16>& dst, size_t off, const float* w, int row0, int nrows, int K, int valid_rows) {
+  for (int r = 0; r < nrows; ++r)
+    for (int k = 0; k < K + 8; ++k) {
+      const bool ok = (k < K) && (row0 + r < valid_rows);
+      dst[off + (size_t)r * (K + 8) + k] = __float2bfloat16(ok ? w[(size_t)(row0 + r) * K + k] : 0.f);
+    }
+}
+
+int pack_decode_operands(hmocr_engine* e) {
+  const hmocr_config& c = e->cfg;
+  const int d = c.d_model, ff = c.dim_feedforward, V = c.vocab_size, L = c.num_layers;
+  HM_CHECK(d == 256 && ff == 512 && c.nhead == 8,
+           "the persistent decode kernel is specialised for d_model=256, nhead=8, dim_feedforward=512 "
+           "(reference config.py:19-21); got %d/%d/%d", d, c.nhead, ff);
+  std::vector<__nv_bfloat16> blob((size_t)L * 8 * DP_LAYER_CTA_BYTES / 2);
+  std::vector<float> fpar((size_t)L * DP_FP_LAYER);
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "decoder.decoder.layers." + std::to_string(l) + ".";
+    const HostTensor *sin, *sinb, *so, *sob, *cin, *cinb, *co, *cob, *w1, *b1, *w2, *b2;
+    HM_TRY(need(e, p + "self_attn.in_proj_weight", {3 * d, d}, &sin));
+    HM_TRY(need(e, p + "self_attn.in_proj_bias", {3 * d}, &sinb));
+    HM_TRY(need(e, p + "self_attn.out_proj.weight", {d, d}, &so));
+    HM_TRY(need(e, p + "self_attn.out_proj.bias", {d}, &sob));
+    HM_TRY(need(e, p + "multihead_attn.in_proj_weight", {3 * d, d}, &cin));
+    HM_TRY(need(e, p + "multihead_attn.in_proj_bias", {3 * d}, &cinb));
+    HM_TRY(need(e, p + "multihead_attn.out_proj.weight", {d, d}, &co));
+    HM_TRY(need(e, p + "multihead_attn.out_proj.bias", {d}, &cob));
+    HM_TRY(need(e, p + "linear1.weight", {ff, d}, &w1));
+    HM_TRY(need(e, p + "linear1.bias", {ff}, &b1));
+    HM_TRY(need(e, p + "linear2.weight", {d, ff}, &w2));
+    HM_TRY(need(e, p + "linear2.bias", {d}, &b2));
+    for (int ct = 0; ct < 8; ++ct) {
+      size_t off = ((size_t)l * 8 + ct) * (DP_LAYER_CTA_BYTES / 2);
+      for (int part = 0; part < 3; ++part) {           // q, k, v rows of head ct
+        pack_rows(blob, off, sin->f.data(), part * d + ct * 32, 32, d, 3 * d);
+        off += DP_CH_ATT / 2;
+      }
+      pack_rows(blob, off, so->f.data(), ct * 32, 32, d, d); off += DP_CH_ATT / 2;
+      pack_rows(blob, off, cin->f.data(), ct * 32, 32, d, 3 * d); off += DP_CH_ATT / 2;
+      pack_rows(blob, off, co->f.data(), ct * 32, 32, d, d); off += DP_CH_ATT / 2;
+      pack_rows(blob, off, w1->f.data(), ct * 64, 64, d, ff); off += DP_CH_F1 / 2;
+      pack_rows(blob, off, w2->f.data(), ct * 32, 32, ff, d);
+    }
+    float* fp = &fpar[(size_t)l * DP_FP_LAYER];
+    memcpy(fp + DP_FP_BIN, sinb->f.data(), sizeof(float) * 3 * d);
+    memcpy(fp + DP_FP_BO, sob->f.data(), sizeof(float) * d);
+    memcpy(fp + DP_FP_BCQ, cinb->f.data(), sizeof(float) * d);
+    memcpy(fp + DP_FP_BCO, cob->f.data(), sizeof(float) * d);
+    memcpy(fp + DP_FP_B1, b1->f.data(), sizeof(float) * ff);
+    memcpy(fp + DP_FP_B2, b2->f.data(), sizeof(float) * d);
+    const char* ln[3] = {"norm1", "norm2", "norm3"};
+    const int og[3] = {DP_FP_LN1G, DP_FP_LN2G, DP_FP_LN3G}, ob[3] = {DP_FP_LN1B, DP_FP_LN2B, DP_FP_LN3B};
+    for (int i = 0; i < 3; ++i) {
+      const HostTensor *g, *b;
+      HM_TRY(need(e, p + ln[i] + ".weight", {d}, &g));
+      HM_TRY(need(e, p + ln[i] + ".bias", {d}, &b));
+      memcpy(fp + og[i], g->f.data(), sizeof(float) * d);
+      memcpy(fp + ob[i], b->f.data(), sizeof(float) * d);
+    }
+  }
+  e->dp_fc_chunks = (V + 511) / 512;
+  const int cols_per_cta = e->dp_fc_chunks * 64;
+  std::vector<__nv_bfloat16> fcb((size_t)8 * e->dp_fc_chunks * DP_CH_FC / 2);
+  std::vector<float> fcbias((size_t)8 * cols_per_cta, 0.f);
+  {
+    const HostTensor *w, *b;
+    HM_TRY(need(e, "decoder.fc_out.weight", {V, d}, &w));
+    HM_TRY(need(e, "decoder.fc_out.bias", {V}, &b));
+    for (int ct = 0; ct < 8; ++ct)
+      for (int j = 0; j < e->dp_fc_chunks; ++j)
+        pack_rows(fcb, ((size_t)ct * e->dp_fc_chunks + j) * (DP_CH_FC / 2), w->f.data(), ct * cols_per_cta + j * 64, 64,
+                  d, V);
+    memcpy(fcbias.data(), b->f.data(), sizeof(float) * V);
+  }
+  void* q;
+  HM_TRY(arena_alloc(e, blob.size() * 2, &q));
+  HM_CUDA(cudaMemcpy(q, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice));
+  e->dp_wblob = static_cast<uint8_t*>(q);
+  HM_TRY(arena_alloc(e, fcb.size() * 2, &q));
+  HM_CUDA(cudaMemcpy(q, fcb.data(), fcb.size() * 2, cudaMemcpyHostToDevice));
+  e->dp_fcblob = static_cast<uint8_t*>(q);
+  HM_TRY(upload_f32(e, fpar.data(), fpar.size(), &e->dp_fparams));
+  HM_TRY(upload_f32(e, fcbias.data(), fcbias.size(), &e->dp_fcbias));
+  return 0;
+}
+
+// greedy decode with the persistent cluster kernel: a few launches of `steps_per_launch` steps, the
+// host only polls the all-finished flag of the PREVIOUS launch (the GPU never idles)
+int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int64_t* tokens,
+                        float* logprob, int32_t* steps, cudaStream_t st) {
+  const int nh = e->cfg.nhead, L = e->cfg.num_layers, rows = B;
+  __nv_bfloat16 *memkv, *memk, *memv, *kcache, *vcache;
+  DecodeState* state;
+  uint8_t* finished;
+  const int tmax = e->cfg.max_seq_len;
+  const size_t mem_elems = (size_t)B * MEM_S * e->ca_kv.n;
+  HM_TRY(ws_get(e, "gen.memkv", mem_elems, &memkv));
+  HM_TRY(ws_get(e, "gen.memk", mem_elems / 2, &memk));
+  HM_TRY(ws_get(e, "gen.memv", mem_elems / 2, &memv));
+  const size_t cache_elems = (size_t)L * rows * nh * tmax * 32;
+  HM_TRY(ws_get(e, "gen.kcache", cache_elems, &kcache));
+  HM_TRY(ws_get(e, "gen.vcache", cache_elems, &vcache));
+  HM_TRY(ws_get(e, "gen.state", 1, &state));
+  HM_TRY(ws_get(e, "gen.finished", rows, &finished));
+  HM_TRY(project_memory(e, enc16, B, memkv, st));
+  HM_TRY(repack_memkv(st, memkv, B, L, memk, memv));
+  HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
+  DecPersistParams p;
+  p.wblob = e->dp_wblob; p.fcblob = e->dp_fcblob; p.fparams = e->dp_fparams; p.fc_bias = e->dp_fcbias;
+  p.emb = e->emb; p.pos = e->pos; p.kcache = kcache; p.vcache = vcache; p.memk = memk; p.memv = memv;
+  p.tokens = tokens; p.logprob = logprob; p.finished = finished; p.state = state;
+  p.rows = rows; p.images = B; p.beam = 1; p.num_layers = L; p.fc_chunks = e->dp_fc_chunks;
+  p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
+  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id;
+  const int chunk = e->steps_per_launch > 0 ? e->steps_per_launch : 16;
+  bool done = false;
+  int poll_idx = 0;
+  for (int s0 = 0; s0 < max_len && !done; s0 += chunk, ++poll_idx) {
+    const int s1 = (s0 + chunk < max_len) ? s0 + chunk : max_len;
+    HM_TRY(decode_persistent_launch(st, p, s0, s1));
+    const int slot = poll_idx & 1;
+    HM_CUDA(cudaMemcpyAsync(&e->pinned_state[slot], state, sizeof(DecodeState), cudaMemcpyDeviceToHost, st));
+    HM_CUDA(cudaEventRecord(e->poll_ev[slot], st));
+    if (poll_idx >= 1) {
+      const int prev = (poll_idx - 1) & 1;
+      HM_CUDA(cudaEventSynchronize(e->poll_ev[prev]));
+      if (e->pinned_state[prev].steps_executed > 0) done = true;
+    }
+  }
+  HM_TRY(finalize_decode(st, state, tokens, max_len + 1, rows, max_len, e->cfg.pad_id, logprob, steps));
   return 0;
 }
 
@@ -541,7 +689,8 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   const int d = c.d_model, ff = c.dim_feedforward, V = c.vocab_size;
   size_t total = 0;
   for (auto& kv : e->host) total += kv.second.f.size() * 4 + 1024;
-  e->arena_cap = total + (size_t)e->vpad * d * 4 + (size_t)c.num_layers * 2 * d * (d + 1) * 4 + (64u << 20);
+  e->arena_cap = total + (size_t)e->vpad * d * 4 + (size_t)c.num_layers * 2 * d * (d + 1) * 4 + (64u << 20) +
+                 (size_t)c.num_layers * 8 * DP_LAYER_CTA_BYTES + (size_t)(V / 512 + 1) * 8 * DP_CH_FC + (size_t)c.num_layers * DP_FP_LAYER * 4;
   HM_CUDA(cudaMalloc(&e->arena, e->arena_cap));
   e->arena_used = 0;
 
@@ -620,8 +769,25 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
     memcpy(bp.data(), b->f.data(), sizeof(float) * V);
     HM_TRY(upload_lin_rows(e, wp.data(), bp.data(), e->vpad, d, &e->fc));
   }
+  HM_TRY(pack_decode_operands(e));
+  HM_TRY(decode_persistent_init());
   e->host.clear();
   e->finalized = true;
+  return 0;
+}
+
+HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
+  HM_CHECK(e != nullptr && name != nullptr, "hmocr_set_option: null argument");
+  const std::string n(name);
+  if (n == "decode_impl") {
+    HM_CHECK(value == 0 || value == 1, "decode_impl must be 0 (persistent cluster kernel) or 1 (step graph)");
+    e->decode_impl = value;
+  } else if (n == "steps_per_launch") {
+    HM_CHECK(value >= 1 && value <= 256, "steps_per_launch must be in [1,256]");
+    e->steps_per_launch = value;
+  } else {
+    HM_CHECK(false, "unknown option '%s'", name);
+  }
   return 0;
 }
 

@@ -255,6 +255,10 @@ class FormulaRecognitionModel:
             return tokens[:, : n + 1], n, out_lp, score
         return tokens[:, : n + 1], n, out_lp
 
+    def set_option(self, name: str, value: int) -> None:
+        """Engine options of ``hmocr_set_option`` (``decode_impl``, ``steps_per_launch``)."""
+        _lib.check(self._eng.lib.hmocr_set_option(self._eng.handle, name.encode(), int(value)), "hmocr_set_option")
+
     def last_timings_ms(self) -> Tuple[float, float]:
         enc, dec = C.c_float(), C.c_float()
         _lib.check(self._eng.lib.hmocr_last_timings(self._eng.handle, C.byref(enc), C.byref(dec)), "hmocr_last_timings")

@@ -60,6 +60,12 @@ int hmocr_load_weight(hmocr_engine* e, const char* key, const void* data_host, c
                       int dtype);
 int hmocr_finalize_weights(hmocr_engine* e);
 
+/* Engine options (all have working defaults):
+ *   "decode_impl"       0 = persistent thread-block-cluster decode kernel (default)
+ *                       1 = one captured CUDA graph of per-layer kernels per step (kept for A/B tests)
+ *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16) */
+int hmocr_set_option(hmocr_engine* e, const char* name, int value);
+
 /* model.encoder(images)                          /root/reference/src/model_swin.py:39-46
  * images_dev f32 [B,1,96,320] -> enc_out_dev f32 [B,30,d_model] */
 int hmocr_encode(hmocr_engine* e, const float* images_dev, int batch, float* enc_out_dev, void* stream);

@@ -148,6 +148,52 @@ def test_incremental_decode_matches_teacher_forced(model, golden_src):
     assert (near < 5e-2).all()
 
 
+def test_persistent_kernel_agrees_with_step_graph(model, golden_src):
+    """Two independent implementations of the decode step (cluster kernel vs per-layer kernels)."""
+    feats = torch.from_numpy(golden_src["features"]).cuda()
+    a_tok, a_steps, a_lp = model.generate(encoder_out=feats, max_len=30, return_logprobs=True)
+    model.set_option("decode_impl", 1)
+    try:
+        b_tok, b_steps, b_lp = model.generate(encoder_out=feats, max_len=30, return_logprobs=True)
+    finally:
+        model.set_option("decode_impl", 0)
+    margin = golden_src["greedy_margin"]
+    for r in range(4):
+        d = (a_tok[r] != b_tok[r]).nonzero()
+        if d.numel():
+            c = int(d[0])
+            assert float(margin[r, c - 1]) < 2 * LOGIT_TOL      # only near-ties may differ
+            n = c - 1
+        else:
+            n = a_steps
+        assert (a_lp[r, :n] - b_lp[r, :n]).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("steps_per_launch", [1, 7, 64])
+def test_persistent_kernel_launch_chunking(model, golden_src, steps_per_launch):
+    """Splitting the step range over several launches must not change a single token."""
+    feats = torch.from_numpy(golden_src["features"]).cuda()
+    ref_tok, ref_steps, _ = model.generate(encoder_out=feats, max_len=40)
+    model.set_option("steps_per_launch", steps_per_launch)
+    try:
+        tok, steps, _ = model.generate(encoder_out=feats, max_len=40)
+    finally:
+        model.set_option("steps_per_launch", 16)
+    assert steps == ref_steps and torch.equal(tok, ref_tok)
+
+
+@pytest.mark.parametrize("B", [1, 15, 17, 33])
+def test_ragged_batches(model, golden_src, B):
+    """Row counts that do not fill a 16-row cluster / 128-row GEMM tile."""
+    from oracle.synth import synth_images
+    imgs = synth_images(4, int(golden_src["images_seed"])).cuda()
+    imgs = imgs.repeat((B + 3) // 4, 1, 1, 1)[:B].contiguous()
+    tok, steps, _ = model.generate(imgs, max_len=24)
+    base, _, _ = model.generate(imgs[:4] if B >= 4 else imgs, max_len=24)
+    for r in range(B):
+        assert torch.equal(tok[r, : base.shape[1]][: tok.shape[1]], base[r % 4 if B >= 4 else r, : tok.shape[1]])
+
+
 def test_errors_are_loud(model):
     with pytest.raises(ValueError):
         model.encoder(torch.zeros(1, 3, 96, 320))
