@@ -28,6 +28,8 @@ SIGNATURES = {
     "hmocr_load_weight": (_i, [_p, C.c_char_p, _p, _i64p, _i, _i]),
     "hmocr_finalize_weights": (_i, [_p]),
     "hmocr_set_option": (_i, [_p, C.c_char_p, _i]),
+    "hmocr_decode_max_clusters": (_i, [C.POINTER(C.c_int)]),
+    "hmocr_read_trace": (_i, [_p, _i64p, _i]),
     "hmocr_encode": (_i, [_p, _p, _i, _p, _p]),
     "hmocr_decoder_forward": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "hmocr_generate": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -4,50 +4,60 @@
 // DecoderTransformer.forward step (src/model_swin.py:72-88, 8 x torch TransformerDecoderLayer,
 // post-LN) + fc_out + argmax — for a range of steps [t_begin, t_end) in ONE launch.
 //
-// Mapping: a thread-block CLUSTER of 8 CTAs owns 16 sequences end to end.  CTA rank c is
-//   * attention head c (self- and cross-attention of its 16 rows for that head), and
+// Mapping: a thread-block CLUSTER of 8 CTAs owns up to 16 sequences end to end.  CTA rank c is
+//   * attention head c (self- and cross-attention of the cluster's rows for that head), and
 //   * the c-th 1/8 column slice of every projection (q/k/v of head c, 32 columns of out_proj,
 //     64 columns of linear1, 32 of linear2, V/8 vocabulary columns of fc_out).
 // So each SM streams only 1/8 of the decoder weights per step (1.6 MB instead of 13 MB): the
-// weight slices are pre-packed per (layer, CTA) and arrive in shared memory through a 4-slot ring
-// of cp.async.bulk (TMA) copies issued 3 chunks ahead, completion on mbarriers.  The 16-row
-// activations are exchanged between the 8 CTAs through distributed shared memory
+// weight slices are pre-packed per (layer, CTA) in 16.5 KB chunks and arrive in shared memory
+// through a 3-slot ring of cp.async.bulk (TMA) copies, completion on mbarriers.  The activations of
+// the cluster's rows are exchanged between the 8 CTAs through distributed shared memory
 // (st.shared::cluster into every peer) and ordered by hardware cluster barriers
 // (barrier.cluster), 6 per layer + 1 per step; no grid-wide synchronisation, no global-memory
-// round trip, no host involvement between steps.  M = 16 rows is exactly one mma.sync m16n8k16
-// tile; the step is bandwidth/latency bound (13-15 MFLOP per token), so tensor-core rate is
-// irrelevant here and tcgen05 (M >= 64) would idle 3/4 of its rows.
-// Self-attention K/V (bf16) are appended to / streamed from the HBM cache with 512-byte
-// coalesced warp loads (8 keys x 64 B per load instruction); the memory K/V of cross-attention
-// are read the same way from a [layer][image][head][30][32] repack.
+// round trip, no host involvement between steps.  16 rows are exactly one mma.sync m16n8k16 tile;
+// the step is bandwidth/latency bound (13-15 MFLOP per token), so tensor-core rate is irrelevant
+// here and tcgen05 (M >= 64) would idle most of its rows.
+//
+// Occupancy is part of the design: the CTA uses 105 KB of shared memory and <= 128 registers so
+// that TWO CTAs (of different clusters) share an SM and 33 clusters are co-resident on a B200
+// (only 15 fit at one CTA per SM).  B=256 therefore runs as 32 clusters x 8 rows in a single wave,
+// and while one CTA of an SM waits on a cluster barrier or on K/V from HBM the other one computes.
+//
+// Self-attention K/V (bf16) are appended to / streamed from the HBM cache in a single pass
+// (online softmax) with 512-byte coalesced warp loads, 8 independent 16-byte loads in flight per
+// lane; the cache rows of the NEXT layer are pulled into L2 (cp.async.bulk.prefetch.L2) while the
+// current layer's projections run.  The memory K/V of cross-attention are read the same way from a
+// [layer][image][head][30][32] repack.
 #include "decode_persistent.cuh"
 
 namespace hmocr {
 namespace {
 
-constexpr int ROWS = 16, CL = 8, THREADS = 256;
+constexpr int CL = 8, THREADS = 256, R = 16, NSLOT = 3;
 constexpr int D = 256, FF = 512, HD = 32, NH = 8, MEM_S = 30;
 constexpr int PD = D + 8, PF = FF + 8;            // padded operand pitches (elements): conflict-free ldmatrix
-constexpr int NSLOT = 4, PRE = 3;
-constexpr int SLOT = DP_CH_F1;
 constexpr float ATT_SCALE = 0.17677669529663687f;
 constexpr float LN_EPS = 1e-5f;
 
 struct __align__(16) Partial { float m; int idx; float s; int pad; };
 
 struct Smem {
-  alignas(128) uint8_t slot[NSLOT][SLOT];
-  alignas(16) float x32[ROWS][D];          // residual stream (replicated in every CTA of the cluster)
-  alignas(16) float y32[ROWS][D];          // pre-LayerNorm rows gathered from the 8 column slices
-  alignas(16) __nv_bfloat16 xa[ROWS][PD];  // LayerNorm output, bf16 A operand
-  alignas(16) __nv_bfloat16 ctxf[ROWS][PD];   // attention context gathered from the 8 heads
-  alignas(16) __nv_bfloat16 hf[ROWS][PF];  // relu(linear1) gathered from the 8 slices
-  alignas(16) float qs[ROWS][HD];          // this head's scaled query
-  Partial part[CL][ROWS];                  // per-CTA argmax / sum-exp partials (gathered)
-  Partial wpart[8][ROWS];                  // per-warp partials
-  int tok[ROWS];
+  alignas(128) uint8_t slot[NSLOT][DP_CHUNK];
+  alignas(16) float y32[R][D];             // pre-LayerNorm rows gathered from the 8 column slices
+  alignas(16) __nv_bfloat16 xa[R][PD];     // LayerNorm output (full rows), bf16 A operand
+  alignas(16) __nv_bfloat16 hf[R][PF];     // relu(linear1) gathered from the 8 slices; its first R*PD
+                                           // elements double as the gathered attention context
+  alignas(16) float x32s[R][32];           // fp32 residual stream, this CTA's 32-column slice only
+  alignas(16) float qs[R][HD];             // this head's scaled query
+  Partial part[CL][R];                     // per-CTA argmax / sum-exp partials (gathered)
+  Partial wpart[8][R];                     // per-warp partials
+  int tok[R];
+  alignas(16) float fpar[2][DP_FPC];       // this CTA's bias slices of layer l / l+1
+  alignas(16) float fcb[DP_FCB_MAX];       // this CTA's slice of fc_out.bias
   alignas(8) uint64_t full[NSLOT];
+  alignas(8) uint64_t fpbar[2];
 };
+static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs must fit one SM");
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -125,60 +135,106 @@ __device__ __forceinline__ float dot8(const float (&q)[8], const uint4 u) {
   s = fmaf(q[4], c.x, s); s = fmaf(q[5], c.y, s); s = fmaf(q[6], d.x, s); s = fmaf(q[7], d.y, s);
   return s;
 }
+__device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4 u) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  acc[0] = fmaf(p, a.x, acc[0]); acc[1] = fmaf(p, a.y, acc[1]); acc[2] = fmaf(p, b.x, acc[2]);
+  acc[3] = fmaf(p, b.y, acc[3]); acc[4] = fmaf(p, c.x, acc[4]); acc[5] = fmaf(p, c.y, acc[5]);
+  acc[6] = fmaf(p, d.x, acc[6]); acc[7] = fmaf(p, d.y, acc[7]);
+}
 
-// One query row against n keys.  Lane = (key group jg = lane/4, dim chunk dc = lane%4): every load
-// instruction of the warp fetches 8 consecutive 64-byte K (or V) rows = 512 contiguous bytes.
-// out[0..7] = context channels dc*8.. (valid in every lane after the key-group reduction).
-template <int NI>
-__device__ __forceinline__ void attend_row(const float* q, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int n,
-                                           int lane, float (&out)[8]) {
-  const int jg = lane >> 2, dc = lane & 3;
-  float qv[8];
+struct OnlineRow {       // per-lane online-softmax state of one query row over this lane's key group
+  float m, den, acc[8];
+  __device__ __forceinline__ void init() {
+    m = -INFINITY; den = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) qv[e] = q[dc * 8 + e];
-  float sc[NI];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    sc[i] = -INFINITY;
-    if (i * 8 < n) {                                   // warp-uniform
-      const int j = jg + 8 * i;
-      float a = 0.f;
-      if (j < n) a = dot8(qv, __ldcg(reinterpret_cast<const uint4*>(Kb + (size_t)j * HD + dc * 8)));
-      a += __shfl_xor_sync(0xffffffffu, a, 1);
-      a += __shfl_xor_sync(0xffffffffu, a, 2);
-      if (j < n) { sc[i] = a; mx = fmaxf(mx, a); }
-    }
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   }
-  mx = warp_max(mx);
-  float den = 0.f;
-  float acc[8];
+  template <int G>
+  __device__ __forceinline__ void update(const float (&s)[G], const uint4 (&v)[G]) {
+    float mn = m;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int u = 0; u < G; ++u) mn = fmaxf(mn, s[u]);
+    if (mn == -INFINITY) return;
+    const float corr = __expf(m - mn);
+    den *= corr;
 #pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    if (i * 8 < n) {
-      const int j = jg + 8 * i;
-      if (j < n) {
-        const float p = __expf(sc[i] - mx);
-        den += p;
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(Vb + (size_t)j * HD + dc * 8));
-        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-        acc[0] = fmaf(p, a.x, acc[0]); acc[1] = fmaf(p, a.y, acc[1]); acc[2] = fmaf(p, b.x, acc[2]);
-        acc[3] = fmaf(p, b.y, acc[3]); acc[4] = fmaf(p, c.x, acc[4]); acc[5] = fmaf(p, c.y, acc[5]);
-        acc[6] = fmaf(p, d.x, acc[6]); acc[7] = fmaf(p, d.y, acc[7]);
+    for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const float p = __expf(s[u] - mn);
+      den += p;
+      axpy8(acc, p, v[u]);
+    }
+    m = mn;
+  }
+  // combine the 8 key groups (lanes with the same lane%4) and normalise
+  __device__ __forceinline__ void finish(float (&out)[8]) {
+    float M = m;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    const float sc = (m == -INFINITY) ? 0.f : __expf(m - M);
+    den *= sc;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= sc;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = acc[e] * inv;
+  }
+};
+
+// NR (1 or 2) query rows against n keys each, one pass.  Lane = (key group jg = lane/4, dim chunk
+// dc = lane%4): every load instruction of the warp fetches 8 consecutive 64-byte K (or V) rows =
+// 512 contiguous bytes; 8 independent 16-byte loads per lane (K and V of 4/NR key blocks x NR rows)
+// are issued before the first use.
+template <int NR, int NI>
+__device__ __forceinline__ void attend(const float* (&q)[NR], const __nv_bfloat16* (&K)[NR],
+                                       const __nv_bfloat16* (&V)[NR], int n, int lane, float (&out)[NR][8]) {
+  constexpr int G = 4 / NR;
+  const int jg = lane >> 2, dc = lane & 3;
+  float qv[NR][8];
+  OnlineRow row[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    row[r].init();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qv[r][e] = q[r][dc * 8 + e];
+  }
+#pragma unroll
+  for (int i0 = 0; i0 < NI; i0 += G) {
+    if (i0 * 8 < n) {                                   // warp-uniform
+      uint4 kk[NR][G], vv[NR][G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int j = min(jg + 8 * (i0 + u), n - 1);    // clamped: always a valid row, masked below
+        const size_t off = (size_t)j * HD + dc * 8;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          kk[r][u] = __ldcg(reinterpret_cast<const uint4*>(K[r] + off));
+          vv[r][u] = __ldcg(reinterpret_cast<const uint4*>(V[r] + off));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        float sc[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          float a = dot8(qv[r], kk[r][u]);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          sc[u] = ((jg + 8 * (i0 + u)) < n) ? a : -INFINITY;
+        }
+        row[r].template update<G>(sc, vv[r]);
       }
     }
   }
 #pragma unroll
-  for (int o = 4; o < 32; o <<= 1) {
-    den += __shfl_xor_sync(0xffffffffu, den, o);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-  }
-  const float inv = 1.0f / den;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = acc[e] * inv;
+  for (int r = 0; r < NR; ++r) row[r].finish(out[r]);
 }
 
 __device__ __forceinline__ void merge_partial(Partial& a, const Partial& b) {
@@ -196,82 +252,123 @@ __device__ __forceinline__ void update_partial(Partial& a, float v, int idx) {
   else a.s += __expf(v - a.m);
 }
 
+struct LnRegs { float4 g0, g1, b0, b1; };
+
 template <int NI>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  __nv_bfloat16(*ctxf)[PD] = reinterpret_cast<__nv_bfloat16(*)[PD]>(&s.hf[0][0]);   // aliases hf (see Smem)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = (int)cluster_ctarank();              // column slice == attention head
-  const int row0 = (blockIdx.x / CL) * ROWS;
+  const int row0 = (blockIdx.x / CL) * p.rows_per_cluster;
+  const int nrows = min(p.rows_per_cluster, p.rows - row0);     // valid rows of this cluster (1..16)
   const int g4 = lane >> 2, t4 = lane & 3;           // mma fragment coordinates
   const int L = p.num_layers;
-  const int cps = 8 * L + p.fc_chunks;               // weight chunks per step
+  const int cps = DP_LAYER_CHUNKS * L + p.fc_chunks; // weight chunks per step
   const int total_chunks = (t_end - t_begin) * cps;
-  const int cols_per_cta = p.fc_chunks * 64;
+  const int cols_per_cta = p.fc_chunks * 32;
 
-  auto issue = [&](int gi) {
-    const int n = gi % cps;
+  // The copy issuer is lane 0 of warp 7 (a warp that idles in the 4-tile GEMM phases), so issuing never
+  // sits on warp 0's path.  Its cursor is kept incrementally (no integer division on the hot path).
+  constexpr int ISSUER = 7 * 32;
+  int issued = 0, iss_n = 0, iss_slot = 0;           // meaningful in the issuer thread only
+  const uint8_t* iss_src = p.wblob + (size_t)c * DP_LAYER_CTA_BYTES;
+  const int layer_chunks_total = DP_LAYER_CHUNKS * L;
+
+  auto issue_next = [&]() {
+    uint32_t bytes = DP_CHUNK;
     const uint8_t* src;
-    uint32_t bytes;
-    if (n < 8 * L) {
-      const int l = n >> 3, ch = n & 7;
-      src = p.wblob + ((size_t)l * CL + c) * DP_LAYER_CTA_BYTES +
-            (ch < 6 ? ch * DP_CH_ATT : (ch == 6 ? 6 * DP_CH_ATT : 6 * DP_CH_ATT + DP_CH_F1));
-      bytes = ch < 6 ? DP_CH_ATT : (ch == 6 ? DP_CH_F1 : DP_CH_F2);
+    if (iss_n < layer_chunks_total) {
+      src = iss_src;
+      const int ch = iss_n % DP_LAYER_CHUNKS;         // compile-time divisor
+      if (ch >= 8) bytes = DP_CHUNK_F2;               // the two linear2 pieces
+      iss_src += bytes;
+      if (ch == DP_LAYER_CHUNKS - 1) iss_src += (size_t)(CL - 1) * DP_LAYER_CTA_BYTES;   // next layer's block
     } else {
-      src = p.fcblob + ((size_t)c * p.fc_chunks + (n - 8 * L)) * DP_CH_FC;
-      bytes = DP_CH_FC;
+      src = p.fcblob + ((size_t)c * p.fc_chunks + (iss_n - layer_chunks_total)) * DP_CHUNK;
     }
-    uint64_t* bar = &s.full[gi & (NSLOT - 1)];
+    uint64_t* bar = &s.full[iss_slot];
     mbar_expect_tx(bar, bytes);
-    bulk_g2s(s.slot[gi & (NSLOT - 1)], src, bytes, bar);
+    bulk_g2s(s.slot[iss_slot], src, bytes, bar);
+    if (++iss_slot == NSLOT) iss_slot = 0;
+    if (++iss_n == cps) { iss_n = 0; iss_src = p.wblob + (size_t)c * DP_LAYER_CTA_BYTES; }
+    ++issued;
   };
-  // wait for chunk g (and keep the ring PRE chunks ahead); the slot being refilled held chunk g-1,
-  // whose readers all passed a block/cluster barrier before anyone gets here
-  auto acquire = [&](int g) -> const __nv_bfloat16* {
-    if (tid == 0 && g + PRE < total_chunks) issue(g + PRE);
-    mbar_wait(&s.full[g & (NSLOT - 1)], (g >> 2) & 1);
-    return reinterpret_cast<const __nv_bfloat16*>(s.slot[g & (NSLOT - 1)]);
+  // Refill the ring: every chunk < g has been released (its readers passed a block or cluster barrier),
+  // so chunks up to g + NSLOT - 1 may be in flight.
+  auto refill = [&](int g) {
+    if (tid == ISSUER) {
+      while (issued < total_chunks && issued < g + NSLOT) issue_next();
+    }
+  };
+  auto wait_chunks = [&](int g, int n) {
+    for (int i = 0; i < n; ++i) mbar_wait(&s.full[(g + i) % NSLOT], ((g + i) / NSLOT) & 1);
+  };
+  auto chunk_ptr = [&](int x) { return reinterpret_cast<const __nv_bfloat16*>(s.slot[x % NSLOT]); };
+  // per-layer bias slices of this CTA, double buffered: layer counter gl = step * L + l
+  const int total_layers = (t_end - t_begin) * L;
+  auto issue_fpar = [&](int gl) {
+    if (tid == ISSUER && gl < total_layers) {
+      const int l = gl % L;
+      mbar_expect_tx(&s.fpbar[gl & 1], DP_FPC * 4);
+      bulk_g2s(s.fpar[gl & 1], p.fparams + ((size_t)l * CL + c) * DP_FPC, DP_FPC * 4, &s.fpbar[gl & 1]);
+    }
+  };
+  // LayerNorm gamma/beta of this lane's 8 columns, fetched (L2) a phase ahead of their use
+  auto load_ln = [&](int l, int which) {
+    const float* g = p.lnparams + ((size_t)l * 6 + 2 * which) * D + lane * 8;
+    LnRegs r;
+    r.g0 = __ldg(reinterpret_cast<const float4*>(g));
+    r.g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+    r.b0 = __ldg(reinterpret_cast<const float4*>(g + D));
+    r.b1 = __ldg(reinterpret_cast<const float4*>(g + D + 4));
+    return r;
   };
 
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) mbar_init(&s.full[i], 1);
+    mbar_init(&s.fpbar[0], 1);
+    mbar_init(&s.fpbar[1], 1);
     fence_barrier_init();
   }
-  // x = embedding[token at t_begin] + pos[t_begin]
-  {
+  for (int i = tid; i < cols_per_cta; i += THREADS) s.fcb[i] = p.fc_bias[c * cols_per_cta + i];
+
+  // x = embedding[token] + pos[t]: full rows as the bf16 A operand, this CTA's 32 columns as fp32 residual
+  auto embed_rows = [&](int t, bool from_global) {
     const int r = tid >> 4, c0 = (tid & 15) * 16;
-    const int gr = row0 + r;
-    long long tk = (gr < p.rows) ? p.tokens[(size_t)gr * p.ld_tok + t_begin] : 0;
+    long long tk = 0;
+    const bool ok = r < nrows;
+    if (ok) tk = from_global ? p.tokens[(size_t)(row0 + r) * p.ld_tok + t] : (long long)s.tok[r];
     if (tk < 0 || tk >= p.vocab) tk = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < p.rows) {
+      if (ok) {
         const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * D + c0) + q);
-        const float4 ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)t_begin * D + c0) + q);
+        const float4 ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)t * D + c0) + q);
         v = make_float4(e.x + ps.x, e.y + ps.y, e.z + ps.z, e.w + ps.w);
       }
-      *reinterpret_cast<float4*>(&s.x32[r][c0 + 4 * q]) = v;
       *reinterpret_cast<uint2*>(&s.xa[r][c0 + 4 * q]) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      if ((c0 >> 5) == c) *reinterpret_cast<float4*>(&s.x32s[r][(c0 & 31) + 4 * q]) = v;
     }
-  }
+  };
+  embed_rows(t_begin, true);
   __syncthreads();
-  if (tid == 0)
-    for (int i = 0; i < PRE && i < total_chunks; ++i) issue(i);
   cluster_sync_all();      // every CTA of the cluster is resident and initialised before any DSMEM store
 
-  const uint32_t ctxf_base = smem_u32(&s.ctxf[0][0]);
+  const uint32_t ctxf_base = smem_u32(&s.hf[0][0]);
   const uint32_t y32_base = smem_u32(&s.y32[0][0]);
   const uint32_t hf_base = smem_u32(&s.hf[0][0]);
   const uint32_t part_base = smem_u32(&s.part[0][0]);
 
-  // LayerNorm of the gathered rows: warp w owns rows 2w, 2w+1; lane owns 8 consecutive columns
-  auto layer_norm = [&](const float* gamma, const float* beta) {
+  // LayerNorm of the gathered rows: warp w owns rows w and w+8; lane owns 8 consecutive columns
+  auto layer_norm = [&](const LnRegs& ln) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int r = warp * 2 + rr;
+      const int r = warp + 8 * rr;
+      if (r >= nrows) break;                             // warp-uniform
       const float4 a = *reinterpret_cast<const float4*>(&s.y32[r][lane * 8]);
       const float4 b = *reinterpret_cast<const float4*>(&s.y32[r][lane * 8 + 4]);
       float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -283,194 +380,260 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { v[e] -= mean; sq += v[e] * v[e]; }
       const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + LN_EPS);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + lane * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + lane * 8 + 4));
-      v[0] = v[0] * rstd * g0.x + b0.x; v[1] = v[1] * rstd * g0.y + b0.y; v[2] = v[2] * rstd * g0.z + b0.z;
-      v[3] = v[3] * rstd * g0.w + b0.w; v[4] = v[4] * rstd * g1.x + b1.x; v[5] = v[5] * rstd * g1.y + b1.y;
-      v[6] = v[6] * rstd * g1.z + b1.z; v[7] = v[7] * rstd * g1.w + b1.w;
-      *reinterpret_cast<float4*>(&s.x32[r][lane * 8]) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(&s.x32[r][lane * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+      v[0] = v[0] * rstd * ln.g0.x + ln.b0.x; v[1] = v[1] * rstd * ln.g0.y + ln.b0.y;
+      v[2] = v[2] * rstd * ln.g0.z + ln.b0.z; v[3] = v[3] * rstd * ln.g0.w + ln.b0.w;
+      v[4] = v[4] * rstd * ln.g1.x + ln.b1.x; v[5] = v[5] * rstd * ln.g1.y + ln.b1.y;
+      v[6] = v[6] * rstd * ln.g1.z + ln.b1.z; v[7] = v[7] * rstd * ln.g1.w + ln.b1.w;
+      if ((lane >> 2) == c) {                            // this CTA's residual slice: columns c*32 .. c*32+31
+        *reinterpret_cast<float4*>(&s.x32s[r][(lane & 3) * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(&s.x32s[r][(lane & 3) * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+      }
       *reinterpret_cast<uint4*>(&s.xa[r][lane * 8]) =
           make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
   };
-  // query slice of head c: qs = (xa Wq^T + b) / sqrt(32)
+  // query slice of head c (one chunk, 4 n-tiles): qs = (xa Wq^T + b) / sqrt(32)
   auto project_q = [&](const __nv_bfloat16* W, const float* bias) {
     if (warp < 4) {
       float acc[4];
       gemm_tile<D, PD>(&s.xa[0][0], W, warp, lane, acc);
       const int col = warp * 8 + 2 * t4;
-      const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
+      const float b0 = bias[col], b1 = bias[col + 1];
       s.qs[g4][col] = (acc[0] + b0) * ATT_SCALE; s.qs[g4][col + 1] = (acc[1] + b1) * ATT_SCALE;
       s.qs[g4 + 8][col] = (acc[2] + b0) * ATT_SCALE; s.qs[g4 + 8][col + 1] = (acc[3] + b1) * ATT_SCALE;
     }
   };
-  // out-projection slice (32 columns) + bias + residual -> y32 of every CTA in the cluster
-  auto project_out = [&](const __nv_bfloat16* A, auto gemm, const float* bias) {
-    if (warp < 4) {
-      float acc[4];
-      gemm(A, acc);
-      const int col = c * 32 + warp * 8 + 2 * t4;
-      const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
-      const float y0 = acc[0] + b0 + s.x32[g4][col], y1 = acc[1] + b1 + s.x32[g4][col + 1];
-      const float y2 = acc[2] + b0 + s.x32[g4 + 8][col], y3 = acc[3] + b1 + s.x32[g4 + 8][col + 1];
-      const uint32_t o0 = y32_base + (g4 * D + col) * 4, o1 = y32_base + ((g4 + 8) * D + col) * 4;
+  // y = acc + bias + residual  ->  y32[r][c*32 + lc ..] of every CTA in the cluster (lc: column in the slice)
+  auto scatter_y = [&](const float (&acc)[4], int lc, const float* bias) {
+    const float b0 = bias[lc], b1 = bias[lc + 1];
+    const int col = c * 32 + lc;
+    if (g4 < nrows) {
+      const float y0 = acc[0] + b0 + s.x32s[g4][lc], y1 = acc[1] + b1 + s.x32s[g4][lc + 1];
+      const uint32_t o0 = y32_base + (g4 * D + col) * 4;
 #pragma unroll
-      for (int rk = 0; rk < CL; ++rk) {
-        st_cluster_v2(mapa(o0, rk), __float_as_uint(y0), __float_as_uint(y1));
-        st_cluster_v2(mapa(o1, rk), __float_as_uint(y2), __float_as_uint(y3));
-      }
+      for (int rk = 0; rk < CL; ++rk) st_cluster_v2(mapa(o0, rk), __float_as_uint(y0), __float_as_uint(y1));
+    }
+    if (g4 + 8 < nrows) {
+      const float y2 = acc[2] + b0 + s.x32s[g4 + 8][lc], y3 = acc[3] + b1 + s.x32s[g4 + 8][lc + 1];
+      const uint32_t o1 = y32_base + ((g4 + 8) * D + col) * 4;
+#pragma unroll
+      for (int rk = 0; rk < CL; ++rk) st_cluster_v2(mapa(o1, rk), __float_as_uint(y2), __float_as_uint(y3));
     }
   };
-  // attention of rows 2w, 2w+1 for head c; context slice -> ctxf of every CTA
+  // out-projection slice (one chunk, 32 columns) over the gathered context
+  auto project_out = [&](const __nv_bfloat16* W, const float* bias) {
+    if (warp < 4) {
+      float acc[4];
+      gemm_tile<D, PD>(&ctxf[0][0], W, warp, lane, acc);
+      scatter_y(acc, warp * 8 + 2 * t4, bias);
+    }
+  };
+  // attention of rows w (and w+8) for head c; context slice -> ctxf of every CTA
+  auto put_ctx = [&](int r, const float (&o)[8]) {
+    if (lane < 4) {
+      const uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      const uint32_t off = ctxf_base + (r * PD + c * HD + lane * 8) * 2;
+#pragma unroll
+      for (int rk = 0; rk < CL; ++rk) st_cluster_v4(mapa(off, rk), v);
+    }
+  };
   auto attention = [&](auto kv_of_row, int nkeys) {
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = warp * 2 + rr;
-      const int gr = row0 + r;
-      float out[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) out[e] = 0.f;
-      if (gr < p.rows) {                               // warp-uniform
-        const __nv_bfloat16 *Kb, *Vb;
-        kv_of_row(gr, Kb, Vb);
-        attend_row<NI>(&s.qs[r][0], Kb, Vb, nkeys, lane, out);
-      }
-      if (lane < 4) {
-        const uint4 v = make_uint4(pack_bf16(out[0], out[1]), pack_bf16(out[2], out[3]), pack_bf16(out[4], out[5]),
-                                   pack_bf16(out[6], out[7]));
-        const uint32_t o = ctxf_base + (r * PD + c * HD + lane * 8) * 2;
-#pragma unroll
-        for (int rk = 0; rk < CL; ++rk) st_cluster_v4(mapa(o, rk), v);
-      }
+    if (warp >= nrows) return;                             // warp-uniform
+    if (warp + 8 < nrows) {
+      const float* q[2] = {&s.qs[warp][0], &s.qs[warp + 8][0]};
+      const __nv_bfloat16 *K[2], *V[2];
+      kv_of_row(row0 + warp, K[0], V[0]);
+      kv_of_row(row0 + warp + 8, K[1], V[1]);
+      float o[2][8];
+      attend<2, NI>(q, K, V, nkeys, lane, o);
+      put_ctx(warp, o[0]);
+      put_ctx(warp + 8, o[1]);
+    } else {
+      const float* q[1] = {&s.qs[warp][0]};
+      const __nv_bfloat16 *K[1], *V[1];
+      kv_of_row(row0 + warp, K[0], V[0]);
+      float o[1][8];
+      attend<1, NI>(q, K, V, nkeys, lane, o);
+      put_ctx(warp, o[0]);
+    }
+  };
+  // L2 prefetch of K/V rows ahead of their attention: lane -> (row = lane/2, K or V = lane&1) of warp 6
+  auto prefetch_kv = [&](const __nv_bfloat16* kbase, const __nv_bfloat16* vbase, size_t row_stride, int first_row,
+                         int count, int bytes) {
+    if (warp == 6 && bytes >= 16 && (lane >> 1) < count) {
+      const __nv_bfloat16* src = ((lane & 1) ? vbase : kbase) + (size_t)(first_row + (lane >> 1)) * row_stride;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes)
+                   : "memory");
     }
   };
 
   int g = 0;     // weight chunk counter of this launch
+  int gl = 0;    // layer counter of this launch (parity of the fpar double buffer)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  int ti = 0;
+#define TR() do { if (tracing && t == p.trace_step && ti < 1024) p.trace[ti++] = clock64(); } while (0)
+  issue_fpar(0);
+  refill(0);
   for (int t = t_begin; t < t_end; ++t) {
-    for (int l = 0; l < L; ++l) {
-      const float* fp = p.fparams + (size_t)l * DP_FP_LAYER;
+    for (int l = 0; l < L; ++l, ++gl) {
       const size_t cache_l = (size_t)l * p.rows;
-      // ---- self-attention: q, k, v of head c ---------------------------------------------------
-      {
-        const __nv_bfloat16* W = acquire(g);
-        project_q(W, fp + DP_FP_BIN + c * HD);
-        __syncthreads();
-        ++g;
-      }
-#pragma unroll 1
-      for (int kv = 0; kv < 2; ++kv) {
-        const __nv_bfloat16* W = acquire(g);
-        if (warp < 4) {
-          float acc[4];
-          gemm_tile<D, PD>(&s.xa[0][0], W, warp, lane, acc);
-          const int col = warp * 8 + 2 * t4;
-          const float* bias = fp + DP_FP_BIN + (1 + kv) * D + c * HD;
-          const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
-          __nv_bfloat16* cache = kv ? p.vcache : p.kcache;
-          const int r0 = row0 + g4, r1 = row0 + g4 + 8;
-          if (r0 < p.rows)
-            *reinterpret_cast<uint32_t*>(cache + (((cache_l + r0) * NH + c) * p.tmax + t) * HD + col) =
+      issue_fpar(gl + 1);
+      mbar_wait(&s.fpbar[gl & 1], (gl >> 1) & 1);
+      const float* fp = s.fpar[gl & 1];
+      // ---- self-attention: q, k, v of head c (3 chunks, 12 n-tiles over 8 warps) -------------------
+      TR();
+      wait_chunks(g, 3);
+      TR();
+      // cross-attention memory of this layer -> L2 while the self-attention runs
+      prefetch_kv(p.memk + (((size_t)l * p.images) * NH + c) * (size_t)MEM_S * HD,
+                  p.memv + (((size_t)l * p.images) * NH + c) * (size_t)MEM_S * HD, (size_t)NH * MEM_S * HD,
+                  row0 / p.beam, min(nrows, p.images - row0 / p.beam), MEM_S * HD * 2);
+      for (int tt = warp; tt < 12; tt += 8) {
+        const int part = tt >> 2, nt = tt & 3;              // 0 = q, 1 = k, 2 = v
+        float acc[4];
+        gemm_tile<D, PD>(&s.xa[0][0], chunk_ptr(g + part), nt, lane, acc);
+        const int col = nt * 8 + 2 * t4;
+        const float* bias = fp + DPC_BQKV + part * HD;
+        const float b0 = bias[col], b1 = bias[col + 1];
+        if (part == 0) {
+          s.qs[g4][col] = (acc[0] + b0) * ATT_SCALE; s.qs[g4][col + 1] = (acc[1] + b1) * ATT_SCALE;
+          s.qs[g4 + 8][col] = (acc[2] + b0) * ATT_SCALE; s.qs[g4 + 8][col + 1] = (acc[3] + b1) * ATT_SCALE;
+        } else {
+          __nv_bfloat16* cache = (part == 2) ? p.vcache : p.kcache;
+          if (g4 < nrows)
+            *reinterpret_cast<uint32_t*>(cache + (((cache_l + row0 + g4) * NH + c) * p.tmax + t) * HD + col) =
                 pack_bf16(acc[0] + b0, acc[1] + b1);
-          if (r1 < p.rows)
-            *reinterpret_cast<uint32_t*>(cache + (((cache_l + r1) * NH + c) * p.tmax + t) * HD + col) =
+          if (g4 + 8 < nrows)
+            *reinterpret_cast<uint32_t*>(cache + (((cache_l + row0 + g4 + 8) * NH + c) * p.tmax + t) * HD + col) =
                 pack_bf16(acc[2] + b0, acc[3] + b1);
         }
-        __syncthreads();      // also publishes the appended K/V row to the attention warps of this CTA
-        ++g;
       }
+      __syncthreads();      // releases the 3 chunks; publishes qs and the appended K/V row to this CTA
+      g += 3;
+      refill(g);
+      TR();
       attention(
           [&](int gr, const __nv_bfloat16*& Kb, const __nv_bfloat16*& Vb) {
             const size_t off = ((cache_l + gr) * NH + c) * (size_t)p.tmax * HD;
             Kb = p.kcache + off; Vb = p.vcache + off;
           },
           t + 1);
-      cluster_sync_all();                                                        // #1 ctxf complete
-      // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
+      TR();
+      cluster_sync_all();                                                        // #1 context gathered
+      TR();
+      // self-attention cache of the NEXT layer (next step's layer 0 after the last one) -> L2, now that
+      // this layer's K/V burst is over
       {
-        const __nv_bfloat16* W = acquire(g);
-        project_out(&s.ctxf[0][0], [&](const __nv_bfloat16* A, float (&acc)[4]) { gemm_tile<D, PD>(A, W, warp, lane, acc); },
-                    fp + DP_FP_BO);
-        cluster_sync_all();                                                      // #2 y32 complete
-        ++g;
-        layer_norm(fp + DP_FP_LN1G, fp + DP_FP_LN1B);
-        __syncthreads();
-      }
-      // ---- cross-attention over the 30 memory tokens ----------------------------------------------
-      {
-        const __nv_bfloat16* W = acquire(g);
-        project_q(W, fp + DP_FP_BCQ + c * HD);
-        __syncthreads();
-        ++g;
-        attention(
-            [&](int gr, const __nv_bfloat16*& Kb, const __nv_bfloat16*& Vb) {
-              const int img = gr / p.beam;
-              const size_t off = (((size_t)l * p.images + img) * NH + c) * (size_t)MEM_S * HD;
-              Kb = p.memk + off; Vb = p.memv + off;
-            },
-            MEM_S);
-        cluster_sync_all();                                                      // #3
-      }
-      {
-        const __nv_bfloat16* W = acquire(g);
-        project_out(&s.ctxf[0][0], [&](const __nv_bfloat16* A, float (&acc)[4]) { gemm_tile<D, PD>(A, W, warp, lane, acc); },
-                    fp + DP_FP_BCO);
-        cluster_sync_all();                                                      // #4
-        ++g;
-        layer_norm(fp + DP_FP_LN2G, fp + DP_FP_LN2B);
-        __syncthreads();
-      }
-      // ---- feed-forward: 64 columns of linear1 (+ReLU) per CTA, then 32 columns of linear2 ---------
-      {
-        const __nv_bfloat16* W = acquire(g);
-        float acc[4];
-        gemm_tile<D, PD>(&s.xa[0][0], W, warp, lane, acc);
-        const int col = c * 64 + warp * 8 + 2 * t4;
-        const float b0 = __ldg(fp + DP_FP_B1 + col), b1 = __ldg(fp + DP_FP_B1 + col + 1);
-        const uint32_t h0 = pack_bf16(fmaxf(acc[0] + b0, 0.f), fmaxf(acc[1] + b1, 0.f));
-        const uint32_t h1 = pack_bf16(fmaxf(acc[2] + b0, 0.f), fmaxf(acc[3] + b1, 0.f));
-        const uint32_t o0 = hf_base + (g4 * PF + col) * 2, o1 = hf_base + ((g4 + 8) * PF + col) * 2;
-#pragma unroll
-        for (int rk = 0; rk < CL; ++rk) {
-          st_cluster_b32(mapa(o0, rk), h0);
-          st_cluster_b32(mapa(o1, rk), h1);
+        const int ln = (l + 1 < L) ? l + 1 : 0;
+        const int keys = (l + 1 < L) ? t : t + 1;
+        if (keys < p.tmax) {
+          const size_t base = ((size_t)ln * p.rows * NH + c) * (size_t)p.tmax * HD;
+          prefetch_kv(p.kcache + base, p.vcache + base, (size_t)NH * p.tmax * HD, row0, nrows, keys * HD * 2);
         }
-        cluster_sync_all();                                                      // #5 hf complete
-        ++g;
       }
+      // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
+      LnRegs ln = load_ln(l, 0);
+      wait_chunks(g, 1);
+      TR();
+      project_out(chunk_ptr(g), fp + DPC_BO);
+      TR();
+      cluster_sync_all();                                                        // #2 y32 gathered
+      TR();
+      g += 1;
+      refill(g);
+      layer_norm(ln);
+      __syncthreads();
+      TR();
+      // ---- cross-attention over the 30 memory tokens ----------------------------------------------
+      wait_chunks(g, 1);
+      TR();
+      project_q(chunk_ptr(g), fp + DPC_BCQ);
+      __syncthreads();
+      g += 1;
+      refill(g);
+      TR();
+      attention(
+          [&](int gr, const __nv_bfloat16*& Kb, const __nv_bfloat16*& Vb) {
+            const int img = gr / p.beam;
+            const size_t off = (((size_t)l * p.images + img) * NH + c) * (size_t)MEM_S * HD;
+            Kb = p.memk + off; Vb = p.memv + off;
+          },
+          MEM_S);
+      TR();
+      cluster_sync_all();                                                        // #3
+      TR();
+      ln = load_ln(l, 1);
+      wait_chunks(g, 1);
+      TR();
+      project_out(chunk_ptr(g), fp + DPC_BCO);
+      TR();
+      cluster_sync_all();                                                        // #4
+      TR();
+      g += 1;
+      refill(g);
+      layer_norm(ln);
+      __syncthreads();
+      TR();
+      // ---- feed-forward: 64 columns of linear1 (+ReLU) per CTA, then 32 columns of linear2 ---------
+      wait_chunks(g, 2);
+      TR();
       {
-        const __nv_bfloat16* W = acquire(g);
-        project_out(&s.hf[0][0], [&](const __nv_bfloat16* A, float (&acc)[4]) { gemm_tile<FF, PF>(A, W, warp, lane, acc); },
-                    fp + DP_FP_B2);
-        cluster_sync_all();                                                      // #6
-        ++g;
-        layer_norm(fp + DP_FP_LN3G, fp + DP_FP_LN3B);
-        __syncthreads();
+        float acc[4];
+        gemm_tile<D, PD>(&s.xa[0][0], chunk_ptr(g + (warp >> 2)), warp & 3, lane, acc);
+        const int lc = warp * 8 + 2 * t4, col = c * 64 + lc;
+        const float b0 = fp[DPC_B1 + lc], b1 = fp[DPC_B1 + lc + 1];
+        if (g4 < nrows) {
+          const uint32_t h0 = pack_bf16(fmaxf(acc[0] + b0, 0.f), fmaxf(acc[1] + b1, 0.f));
+          const uint32_t o0 = hf_base + (g4 * PF + col) * 2;
+#pragma unroll
+          for (int rk = 0; rk < CL; ++rk) st_cluster_b32(mapa(o0, rk), h0);
+        }
+        if (g4 + 8 < nrows) {
+          const uint32_t h1 = pack_bf16(fmaxf(acc[2] + b0, 0.f), fmaxf(acc[3] + b1, 0.f));
+          const uint32_t o1 = hf_base + ((g4 + 8) * PF + col) * 2;
+#pragma unroll
+          for (int rk = 0; rk < CL; ++rk) st_cluster_b32(mapa(o1, rk), h1);
+        }
       }
+      TR();
+      cluster_sync_all();                                                        // #5 hidden gathered
+      TR();
+      g += 2;
+      refill(g);
+      ln = load_ln(l, 2);
+      wait_chunks(g, 2);
+      TR();
+      if (warp < 4) {
+        float acc[4];
+        gemm_tile<FF, PF>(&s.hf[0][0], chunk_ptr(g + (warp >> 1)), warp & 1, lane, acc);
+        scatter_y(acc, warp * 8 + 2 * t4, fp + DPC_B2);
+      }
+      TR();
+      cluster_sync_all();                                                        // #6
+      TR();
+      g += 2;
+      refill(g);
+      layer_norm(ln);
+      __syncthreads();
+      TR();
     }
-    // ---- fc_out slice + running (max, argmax, sum-exp) ---------------------------------------------
+    // ---- fc_out slice + running (max, argmax, sum-exp); 2 chunks = 64 vocabulary rows per phase -----
+    TR();
     Partial pa, pb;        // rows g4 and g4+8 of this thread's columns
     pa.m = pb.m = -INFINITY; pa.idx = pb.idx = 0x7fffffff; pa.s = pb.s = 0.f; pa.pad = pb.pad = 0;
 #pragma unroll 1
-    for (int ch = 0; ch < p.fc_chunks; ++ch) {
-      const __nv_bfloat16* W = acquire(g);
+    for (int ch = 0; ch < p.fc_chunks; ch += 2) {
+      wait_chunks(g, 2);
+      const int lc = ch * 32 + warp * 8 + 2 * t4;
+      const int v0 = c * cols_per_cta + lc;
+      const float b0 = s.fcb[lc], b1 = s.fcb[lc + 1];
       float acc[4];
-      gemm_tile<D, PD>(&s.xa[0][0], W, warp, lane, acc);
-      const int v0 = c * cols_per_cta + ch * 64 + warp * 8 + 2 * t4;
-      if (v0 < p.vocab) {
-        const float b = __ldg(p.fc_bias + v0);
-        update_partial(pa, acc[0] + b, v0);
-        update_partial(pb, acc[2] + b, v0);
-      }
-      if (v0 + 1 < p.vocab) {
-        const float b = __ldg(p.fc_bias + v0 + 1);
-        update_partial(pa, acc[1] + b, v0 + 1);
-        update_partial(pb, acc[3] + b, v0 + 1);
-      }
+      gemm_tile<D, PD>(&s.xa[0][0], chunk_ptr(g + (warp >> 2)), warp & 3, lane, acc);
+      if (v0 < p.vocab) { update_partial(pa, acc[0] + b0, v0); update_partial(pb, acc[2] + b0, v0); }
+      if (v0 + 1 < p.vocab) { update_partial(pa, acc[1] + b1, v0 + 1); update_partial(pb, acc[3] + b1, v0 + 1); }
       __syncthreads();
-      ++g;
+      g += 2;
+      refill(g);
     }
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
@@ -484,23 +647,25 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     }
     if (t4 == 0) { s.wpart[warp][g4] = pa; s.wpart[warp][g4 + 8] = pb; }
     __syncthreads();
-    if (tid < ROWS) {
+    if (tid < R) {
       Partial a = s.wpart[0][tid];
 #pragma unroll
       for (int w = 1; w < 8; ++w) merge_partial(a, s.wpart[w][tid]);
-      const uint32_t o = part_base + (uint32_t)((c * ROWS + tid) * sizeof(Partial));
+      const uint32_t o = part_base + (uint32_t)((c * R + tid) * sizeof(Partial));
       const uint4 v = make_uint4(__float_as_uint(a.m), (uint32_t)a.idx, __float_as_uint(a.s), 0u);
 #pragma unroll
       for (int rk = 0; rk < CL; ++rk) st_cluster_v4(mapa(o, rk), v);
     }
+    TR();
     cluster_sync_all();                                                          // #7 partials gathered
-    if (tid < ROWS) {
+    TR();
+    if (tid < R) {
       Partial a = s.part[0][tid];
 #pragma unroll
       for (int k = 1; k < CL; ++k) merge_partial(a, s.part[k][tid]);
       s.tok[tid] = a.idx;
       const int gr = row0 + tid;
-      if (c == 0 && gr < p.rows) {
+      if (c == 0 && tid < nrows) {
         p.tokens[(size_t)gr * p.ld_tok + t + 1] = a.idx;
         if (p.logprob != nullptr) p.logprob[(size_t)gr * p.max_len + t] = -logf(a.s);   // log_softmax of the argmax
         if (a.idx == p.eos && !p.finished[gr]) {
@@ -511,20 +676,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
     }
     __syncthreads();
+    TR();
     // ---- next input: embedding[token] + pos[t+1] ------------------------------------------------------
-    if (t + 1 < p.max_pos) {
-      const int r = tid >> 4, c0 = (tid & 15) * 16;
-      const int tk = s.tok[r];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * D + c0) + q);
-        const float4 ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(t + 1) * D + c0) + q);
-        const float4 v = make_float4(e.x + ps.x, e.y + ps.y, e.z + ps.z, e.w + ps.w);
-        *reinterpret_cast<float4*>(&s.x32[r][c0 + 4 * q]) = v;
-        *reinterpret_cast<uint2*>(&s.xa[r][c0 + 4 * q]) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-      }
-    }
+    if (t + 1 < p.max_pos) embed_rows(t + 1, false);
     __syncthreads();
+    TR();
   }
   if (blockIdx.x == 0 && tid == 0) p.state->step = t_end;
   cluster_sync_all();      // no CTA exits while a peer may still address its shared memory
@@ -547,6 +703,8 @@ __global__ void repack_memkv_kernel(const __nv_bfloat16* __restrict__ memkv, int
   }
 }
 
+int g_max_clusters = 0;
+
 }  // namespace
 
 int decode_persistent_init() {
@@ -554,16 +712,42 @@ int decode_persistent_init() {
   if (done) return 0;
   HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL * 64);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = sizeof(Smem);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<20>, &cfg));
+  HM_CHECK(g_max_clusters >= 1, "device cannot host an 8-CTA decode cluster");
   done = true;
   return 0;
 }
 
-int decode_persistent_launch(cudaStream_t st, const DecPersistParams& p, int t_begin, int t_end) {
+int decode_persistent_max_clusters(int* out) {
+  HM_TRY(decode_persistent_init());
+  *out = g_max_clusters;
+  return 0;
+}
+
+int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, int t_end) {
   HM_TRY(decode_persistent_init());
   HM_CHECK(p.tmax <= 256, "decode: max_seq_len %d > 256", p.tmax);
   HM_CHECK(t_begin >= 0 && t_end > t_begin && t_end <= p.tmax, "decode: bad step range [%d,%d)", t_begin, t_end);
-  const int clusters = ceil_div(p.rows, ROWS);
-  dim3 grid(clusters * CL);
+  HM_CHECK(p.fc_chunks % 2 == 0 && p.fc_chunks * 32 <= DP_FCB_MAX, "decode: bad fc_chunks %d", p.fc_chunks);
+  // Rows per cluster: spread the rows over as many co-resident clusters as possible (fewer rows per
+  // cluster = shorter attention per step, same projection latency) without ever needing a second wave
+  // unless the batch exceeds 16 rows x max clusters.
+  int rpc = p.rows_per_cluster;
+  if (rpc <= 0) {
+    rpc = ceil_div(p.rows, g_max_clusters);
+    if (rpc > 16) rpc = 16;
+  }
+  HM_CHECK(rpc >= 1 && rpc <= 16, "decode: rows_per_cluster %d outside [1,16]", rpc);
+  p.rows_per_cluster = rpc;
+  dim3 grid(ceil_div(p.rows, rpc) * CL);
   if (p.tmax <= 160)
     decode_persistent_kernel<20><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
   else

@@ -80,10 +80,12 @@ struct hmocr_engine {
   Lin fc;
   // packed operands of the persistent cluster decode kernel (decode_persistent.cuh)
   uint8_t *dp_wblob = nullptr, *dp_fcblob = nullptr;
-  float *dp_fparams = nullptr, *dp_fcbias = nullptr;
+  float *dp_fparams = nullptr, *dp_fcbias = nullptr, *dp_lnparams = nullptr;
+  int rows_per_cluster = 0;           // 0 = automatic
   int dp_fc_chunks = 0;
   int decode_impl = 0;                // 0 = persistent cluster kernel, 1 = per-kernel step graph
   int steps_per_launch = 16;
+  int trace_step = -1;                // >= 0: record phase-boundary clocks of that decode step
 
   // scratch (grow-only); any reallocation invalidates the captured step graphs
   std::map<std::string, Buf> ws;
@@ -467,7 +469,7 @@ int pack_decode_operands(hmocr_engine* e) {
            "the persistent decode kernel is specialised for d_model=256, nhead=8, dim_feedforward=512 "
            "(reference config.py:19-21); got %d/%d/%d", d, c.nhead, ff);
   std::vector<__nv_bfloat16> blob((size_t)L * 8 * DP_LAYER_CTA_BYTES / 2);
-  std::vector<float> fpar((size_t)L * DP_FP_LAYER);
+  std::vector<float> fpar((size_t)L * 8 * DP_FPC), lnpar((size_t)L * 6 * d);
   for (int l = 0; l < L; ++l) {
     const std::string p = "decoder.decoder.layers." + std::to_string(l) + ".";
     const HostTensor *sin, *sinb, *so, *sob, *cin, *cinb, *co, *cob, *w1, *b1, *w2, *b2;
@@ -487,34 +489,37 @@ int pack_decode_operands(hmocr_engine* e) {
       size_t off = ((size_t)l * 8 + ct) * (DP_LAYER_CTA_BYTES / 2);
       for (int part = 0; part < 3; ++part) {           // q, k, v rows of head ct
         pack_rows(blob, off, sin->f.data(), part * d + ct * 32, 32, d, 3 * d);
-        off += DP_CH_ATT / 2;
+        off += DP_CHUNK / 2;
       }
-      pack_rows(blob, off, so->f.data(), ct * 32, 32, d, d); off += DP_CH_ATT / 2;
-      pack_rows(blob, off, cin->f.data(), ct * 32, 32, d, 3 * d); off += DP_CH_ATT / 2;
-      pack_rows(blob, off, co->f.data(), ct * 32, 32, d, d); off += DP_CH_ATT / 2;
-      pack_rows(blob, off, w1->f.data(), ct * 64, 64, d, ff); off += DP_CH_F1 / 2;
+      pack_rows(blob, off, so->f.data(), ct * 32, 32, d, d); off += DP_CHUNK / 2;
+      pack_rows(blob, off, cin->f.data(), ct * 32, 32, d, 3 * d); off += DP_CHUNK / 2;
+      pack_rows(blob, off, co->f.data(), ct * 32, 32, d, d); off += DP_CHUNK / 2;
+      pack_rows(blob, off, w1->f.data(), ct * 64, 64, d, ff); off += DP_CHUNK;
       pack_rows(blob, off, w2->f.data(), ct * 32, 32, ff, d);
     }
-    float* fp = &fpar[(size_t)l * DP_FP_LAYER];
-    memcpy(fp + DP_FP_BIN, sinb->f.data(), sizeof(float) * 3 * d);
-    memcpy(fp + DP_FP_BO, sob->f.data(), sizeof(float) * d);
-    memcpy(fp + DP_FP_BCQ, cinb->f.data(), sizeof(float) * d);
-    memcpy(fp + DP_FP_BCO, cob->f.data(), sizeof(float) * d);
-    memcpy(fp + DP_FP_B1, b1->f.data(), sizeof(float) * ff);
-    memcpy(fp + DP_FP_B2, b2->f.data(), sizeof(float) * d);
     const char* ln[3] = {"norm1", "norm2", "norm3"};
-    const int og[3] = {DP_FP_LN1G, DP_FP_LN2G, DP_FP_LN3G}, ob[3] = {DP_FP_LN1B, DP_FP_LN2B, DP_FP_LN3B};
     for (int i = 0; i < 3; ++i) {
-      const HostTensor *g, *b;
-      HM_TRY(need(e, p + ln[i] + ".weight", {d}, &g));
-      HM_TRY(need(e, p + ln[i] + ".bias", {d}, &b));
-      memcpy(fp + og[i], g->f.data(), sizeof(float) * d);
-      memcpy(fp + ob[i], b->f.data(), sizeof(float) * d);
+      const HostTensor *lg, *lb;
+      HM_TRY(need(e, p + ln[i] + ".weight", {d}, &lg));
+      HM_TRY(need(e, p + ln[i] + ".bias", {d}, &lb));
+      memcpy(&lnpar[((size_t)l * 6 + 2 * i) * d], lg->f.data(), sizeof(float) * d);
+      memcpy(&lnpar[((size_t)l * 6 + 2 * i + 1) * d], lb->f.data(), sizeof(float) * d);
+    }
+    for (int ct = 0; ct < 8; ++ct) {          // the slices CTA `ct` needs (decode_persistent.cuh DPC_*)
+      float* fp = &fpar[((size_t)l * 8 + ct) * DP_FPC];
+      for (int part = 0; part < 3; ++part)
+        memcpy(fp + DPC_BQKV + part * 32, sinb->f.data() + part * d + ct * 32, sizeof(float) * 32);
+      memcpy(fp + DPC_BO, sob->f.data() + ct * 32, sizeof(float) * 32);
+      memcpy(fp + DPC_BCQ, cinb->f.data() + ct * 32, sizeof(float) * 32);
+      memcpy(fp + DPC_BCO, cob->f.data() + ct * 32, sizeof(float) * 32);
+      memcpy(fp + DPC_B1, b1->f.data() + ct * 64, sizeof(float) * 64);
+      memcpy(fp + DPC_B2, b2->f.data() + ct * 32, sizeof(float) * 32);
     }
   }
-  e->dp_fc_chunks = (V + 511) / 512;
-  const int cols_per_cta = e->dp_fc_chunks * 64;
-  std::vector<__nv_bfloat16> fcb((size_t)8 * e->dp_fc_chunks * DP_CH_FC / 2);
+  HM_CHECK(V <= 8 * DP_FCB_MAX, "vocab_size %d exceeds the persistent decode kernel's limit %d", V, 8 * DP_FCB_MAX);
+  e->dp_fc_chunks = 2 * ((V + 511) / 512);      // 32-row chunks, consumed two per phase
+  const int cols_per_cta = e->dp_fc_chunks * 32;
+  std::vector<__nv_bfloat16> fcb((size_t)8 * e->dp_fc_chunks * DP_CHUNK / 2);
   std::vector<float> fcbias((size_t)8 * cols_per_cta, 0.f);
   {
     const HostTensor *w, *b;
@@ -522,7 +527,7 @@ int pack_decode_operands(hmocr_engine* e) {
     HM_TRY(need(e, "decoder.fc_out.bias", {V}, &b));
     for (int ct = 0; ct < 8; ++ct)
       for (int j = 0; j < e->dp_fc_chunks; ++j)
-        pack_rows(fcb, ((size_t)ct * e->dp_fc_chunks + j) * (DP_CH_FC / 2), w->f.data(), ct * cols_per_cta + j * 64, 64,
+        pack_rows(fcb, ((size_t)ct * e->dp_fc_chunks + j) * (DP_CHUNK / 2), w->f.data(), ct * cols_per_cta + j * 32, 32,
                   d, V);
     memcpy(fcbias.data(), b->f.data(), sizeof(float) * V);
   }
@@ -534,6 +539,7 @@ int pack_decode_operands(hmocr_engine* e) {
   HM_CUDA(cudaMemcpy(q, fcb.data(), fcb.size() * 2, cudaMemcpyHostToDevice));
   e->dp_fcblob = static_cast<uint8_t*>(q);
   HM_TRY(upload_f32(e, fpar.data(), fpar.size(), &e->dp_fparams));
+  HM_TRY(upload_f32(e, lnpar.data(), lnpar.size(), &e->dp_lnparams));
   HM_TRY(upload_f32(e, fcbias.data(), fcbias.size(), &e->dp_fcbias));
   return 0;
 }
@@ -561,11 +567,17 @@ int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int 
   HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   DecPersistParams p;
   p.wblob = e->dp_wblob; p.fcblob = e->dp_fcblob; p.fparams = e->dp_fparams; p.fc_bias = e->dp_fcbias;
+  p.lnparams = e->dp_lnparams; p.rows_per_cluster = e->rows_per_cluster;
   p.emb = e->emb; p.pos = e->pos; p.kcache = kcache; p.vcache = vcache; p.memk = memk; p.memv = memv;
   p.tokens = tokens; p.logprob = logprob; p.finished = finished; p.state = state;
   p.rows = rows; p.images = B; p.beam = 1; p.num_layers = L; p.fc_chunks = e->dp_fc_chunks;
   p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
   p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id;
+  p.trace = nullptr; p.trace_step = e->trace_step;
+  if (e->trace_step >= 0) {
+    HM_TRY(ws_get(e, "gen.trace", 1024, &p.trace));
+    HM_CUDA(cudaMemsetAsync(p.trace, 0, 1024 * sizeof(long long), st));
+  }
   const int chunk = e->steps_per_launch > 0 ? e->steps_per_launch : 16;
   bool done = false;
   int poll_idx = 0;
@@ -690,7 +702,7 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   size_t total = 0;
   for (auto& kv : e->host) total += kv.second.f.size() * 4 + 1024;
   e->arena_cap = total + (size_t)e->vpad * d * 4 + (size_t)c.num_layers * 2 * d * (d + 1) * 4 + (64u << 20) +
-                 (size_t)c.num_layers * 8 * DP_LAYER_CTA_BYTES + (size_t)(V / 512 + 1) * 8 * DP_CH_FC + (size_t)c.num_layers * DP_FP_LAYER * 4;
+                 (size_t)c.num_layers * 8 * DP_LAYER_CTA_BYTES + (size_t)(V / 512 + 1) * 8 * 2 * DP_CHUNK + (size_t)c.num_layers * DP_FP_LAYER * 4;
   HM_CUDA(cudaMalloc(&e->arena, e->arena_cap));
   e->arena_used = 0;
 
@@ -776,6 +788,11 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   return 0;
 }
 
+HM_API int hmocr_decode_max_clusters(int* out) {
+  HM_CHECK(out != nullptr, "null argument");
+  return decode_persistent_max_clusters(out);
+}
+
 HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
   HM_CHECK(e != nullptr && name != nullptr, "hmocr_set_option: null argument");
   const std::string n(name);
@@ -785,9 +802,22 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
   } else if (n == "steps_per_launch") {
     HM_CHECK(value >= 1 && value <= 256, "steps_per_launch must be in [1,256]");
     e->steps_per_launch = value;
+  } else if (n == "rows_per_cluster") {
+    HM_CHECK(value >= 0 && value <= 16, "rows_per_cluster must be in [0,16] (0 = automatic)");
+    e->rows_per_cluster = value;
+  } else if (n == "trace_step") {
+    e->trace_step = value;
   } else {
     HM_CHECK(false, "unknown option '%s'", name);
   }
+  return 0;
+}
+
+HM_API int hmocr_read_trace(hmocr_engine* e, int64_t* out_host, int n) {
+  HM_CHECK(e != nullptr && out_host != nullptr && n >= 1 && n <= 1024, "hmocr_read_trace: bad argument");
+  auto it = e->ws.find("gen.trace");
+  HM_CHECK(it != e->ws.end() && it->second.p != nullptr, "no trace recorded (set option trace_step first)");
+  HM_CUDA(cudaMemcpy(out_host, it->second.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
   return 0;
 }
 

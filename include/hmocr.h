@@ -65,6 +65,13 @@ int hmocr_finalize_weights(hmocr_engine* e);
  *                       1 = one captured CUDA graph of per-layer kernels per step (kept for A/B tests)
  *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16) */
 int hmocr_set_option(hmocr_engine* e, const char* name, int value);
+/* Developer aid: with option "trace_step" = t >= 0 the persistent decode kernel records clock64()
+ * of (cluster 0, CTA 0, thread 0) at every phase boundary of decode step t; this copies the first
+ * n (<= 1024) stamps to the host (profiles/ phase breakdowns come from here). */
+int hmocr_read_trace(hmocr_engine* e, int64_t* out_host, int n);
+
+/* How many 8-CTA decode clusters (16 sequences each) can be co-resident on the current device. */
+int hmocr_decode_max_clusters(int* out);
 
 /* model.encoder(images)                          /root/reference/src/model_swin.py:39-46
  * images_dev f32 [B,1,96,320] -> enc_out_dev f32 [B,30,d_model] */
