@@ -152,6 +152,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib
+    from handwritten_math_ocr_api_b200.parallel import gather_tokens
     from oracle.arch import ModelConfig                  # only for the synthetic workload definition
     from oracle.synth import synth_images, synth_state_dict
 
@@ -168,12 +169,11 @@ def run_ours(args, rank, local_rank, world):
     dev_imgs = host_imgs.to(dev)
     lib = _lib.load()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
-    gathered = torch.empty(world * B, T + 1, dtype=torch.int64, device=dev) if world > 1 else None
 
     def step_device():
         tokens, steps, _ = model.generate(dev_imgs, max_len=T)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, tokens.contiguous())
+            gather_tokens(tokens, pad_id=model.pad_id)          # the path's only collective (NCCL)
         return tokens, steps
 
     def barrier():
@@ -220,7 +220,7 @@ def run_ours(args, rank, local_rank, world):
                                            C.c_void_p(tok_host.data_ptr()), None, C.c_void_p(steps_host.data_ptr()),
                                            None, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "generate_host")
         if world > 1:
-            dist.all_gather_into_tensor(gathered, tok_host.to(dev, non_blocking=True))
+            gather_tokens(tok_host.to(dev, non_blocking=True), pad_id=model.pad_id)
     step_e2e()
     barrier()
     e0 = time.perf_counter()
