@@ -153,8 +153,8 @@ def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib
     from handwritten_math_ocr_api_b200.parallel import gather_tokens
-    from oracle.arch import ModelConfig                  # only for the synthetic workload definition
-    from oracle.synth import synth_images, synth_state_dict
+    from handwritten_math_ocr_api_b200.layout import ModelConfig
+    from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict
 
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")

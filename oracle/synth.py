@@ -1,195 +1,6 @@
-"""Synthetic checkpoint and synthetic stroke images (oracle side, TEST INFRASTRUCTURE ONLY).
-
-The reference ships neither a checkpoint nor a dataset, and torch's CPU
-``normal_`` is not guaranteed bit-identical across CPU generations, so "a fixed random-init
-seed" is realised here as a platform-independent generator: every parameter element is
-``splitmix64(fnv1a(name) ^ seed, index)`` mapped to a uniform float.  The same bytes come out in
-the build container (where the golden vectors are made from the real reference) and on the GPU
-box (where the engine and the oracle are compared).
-
-Every parameter is non-trivial on purpose (LayerNorm gains != 1, all biases != 0, a large
-relative-position table) so that a kernel that drops a term cannot pass parity.
-
-Images follow SURVEY.md section 8(d): uint8 canvas 96x320, white background, 3-12 random-walk
-polylines of 8-40 points, thickness 2-3 px, black ink, then ToTensor + Normalize(0.5, 0.5)
-(``/root/reference/src/predict.py:36-41``) => float32 [B,1,96,320] in [-1, 1].
-"""
-from __future__ import annotations
-
-import math
-from typing import Dict
-
-import numpy as np
-import torch
-
-from .arch import IMG_H, IMG_W, WINDOW, ModelConfig, state_dict_layout
-
-_M64 = (1 << 64) - 1
-
-
-def _fnv1a64(s: str) -> int:
-    h = 0xCBF29CE484222325
-    for b in s.encode():
-        h = ((h ^ b) * 0x100000001B3) & _M64
-    return h
-
-
-def _uniform(name: str, n: int, seed: int) -> np.ndarray:
-    """n deterministic floats in (-1, 1), float64, from integer arithmetic only."""
-    base = np.uint64(_fnv1a64(name) ^ ((seed * 0x9E3779B97F4A7C15) & _M64))
-    with np.errstate(over="ignore"):
-        z = base + (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    v = (z >> np.uint64(40)).astype(np.float64)              # 24 random bits
-    return (v + 0.5) / float(1 << 23) - 1.0
-
-
-def relative_position_index() -> np.ndarray:
-    """((dh+6)*13 + (dw+6)) for every (query, key) pair of a 7x7 window, flattened [2401]
-    (torchvision swin_transformer.py:272-284)."""
-    idx = np.arange(WINDOW * WINDOW)
-    r, c = idx // WINDOW, idx % WINDOW
-    dh = r[:, None] - r[None, :] + WINDOW - 1
-    dw = c[:, None] - c[None, :] + WINDOW - 1
-    return (dh * (2 * WINDOW - 1) + dw).reshape(-1).astype(np.int64)
-
-
-def _scale_for(name: str, shape, cfg: ModelConfig, fc_gain: float) -> tuple:
-    """(kind, scale, offset): value = offset + scale * u, u ~ U(-1,1)."""
-    s3 = math.sqrt(3.0)
-    leaf = name.rsplit(".", 1)[-1]
-    if "relative_position_bias_table" in name:
-        return 1.0, 0.0
-    if "norm" in name and leaf == "weight":
-        return 0.2, 1.0
-    if "norm" in name and leaf == "bias":
-        return 0.1, 0.0
-    if name.endswith("embedding.weight"):
-        return s3, 0.0
-    if name.endswith("pos_encoder.weight"):
-        return s3, 0.0
-    if leaf == "bias" or leaf == "in_proj_bias":
-        return 0.1, 0.0
-    # weights: std = gain / sqrt(fan_in)
-    fan_in = int(np.prod(shape[1:]))
-    gain = 1.0
-    if name.endswith("attn.proj.weight") or name.endswith("mlp.3.weight"):
-        gain = 0.5
-    # decoder sub-layer outputs are kept small so the token/position embedding (not a constant
-    # cross-attention term) drives the next token: greedy decodes wander instead of repeating
-    if name.endswith("self_attn.out_proj.weight") or name.endswith("linear2.weight"):
-        gain = 0.2
-    if name.endswith("multihead_attn.out_proj.weight"):
-        gain = 0.35
-    if name.endswith("fc_out.weight"):
-        gain = fc_gain
-    return gain * s3 / math.sqrt(fan_in), 0.0
-
-
-def synth_state_dict(cfg: ModelConfig | None = None, seed: int = 0, fc_gain: float = 4.0,
-                     eos_bias_sigma: float = 2.5) -> Dict[str, torch.Tensor]:
-    """Reference-layout state dict (517 entries, ``encoder.features.*`` aliasing
-    ``encoder.swin.features.*``) filled with the deterministic synthetic values.
-
-    ``eos_bias_sigma`` lifts ``fc_out.bias[eos]`` by that many logit standard deviations so
-    greedy decodes terminate at varied lengths (0 => essentially never emits EOS, the fixed
-    150-step benchmark workload of SURVEY.md section 8d)."""
-    cfg = cfg or ModelConfig()
-    sd: Dict[str, torch.Tensor] = {}
-    for name, shape, dtype in state_dict_layout(cfg):
-        if name.startswith("encoder.features."):
-            sd[name] = sd["encoder.swin.features." + name[len("encoder.features."):]]
-            continue
-        if name.endswith("relative_position_index"):
-            sd[name] = torch.from_numpy(relative_position_index())
-            continue
-        if name == "decoder.tgt_mask":
-            m = torch.triu(torch.full((cfg.max_seq_len, cfg.max_seq_len), float("-inf")), diagonal=1)
-            sd[name] = m
-            continue
-        n = int(np.prod(shape))
-        scale, offset = _scale_for(name, shape, cfg, fc_gain)
-        vals = (offset + scale * _uniform(name, n, seed)).astype(np.float32).reshape(shape)
-        sd[name] = torch.from_numpy(vals)
-    if eos_bias_sigma:
-        sd["decoder.fc_out.bias"][cfg.eos] += float(eos_bias_sigma) * fc_gain
-    return sd
-
-
-def state_dict_checksum(sd: Dict[str, torch.Tensor]) -> str:
-    """Order-independent 64-bit checksum of the parameter BYTES (to prove two boxes hold the
-    same checkpoint)."""
-    acc = 0
-    for k in sorted(sd):
-        if k.startswith("encoder.features."):
-            continue
-        a = sd[k].detach().cpu().contiguous().numpy().view(np.uint8)
-        h = _fnv1a64(k)
-        # 64-bit folded sum of the bytes viewed as uint64 words (padded)
-        pad = (-a.size) % 8
-        w = np.concatenate([a.reshape(-1), np.zeros(pad, np.uint8)]).view(np.uint64)
-        with np.errstate(over="ignore"):
-            s = int(np.bitwise_xor.reduce(w * (np.arange(1, w.size + 1, dtype=np.uint64) | np.uint64(1))))
-        acc = (acc + ((h ^ s) * 0x9E3779B97F4A7C15)) & _M64
-    return f"{acc:016x}"
-
-
-# ---------------------------------------------------------------------------------------------
-# images
-# ---------------------------------------------------------------------------------------------
-
-def _draw_segment(canvas: np.ndarray, x0, y0, x1, y1, thick: float) -> None:
-    h, w = canvas.shape
-    r = thick / 2.0
-    xa, xb = int(math.floor(min(x0, x1) - r - 1)), int(math.ceil(max(x0, x1) + r + 1))
-    ya, yb = int(math.floor(min(y0, y1) - r - 1)), int(math.ceil(max(y0, y1) + r + 1))
-    xa, xb, ya, yb = max(xa, 0), min(xb, w - 1), max(ya, 0), min(yb, h - 1)
-    if xa > xb or ya > yb:
-        return
-    ys, xs = np.mgrid[ya:yb + 1, xa:xb + 1].astype(np.float64)
-    dx, dy = x1 - x0, y1 - y0
-    L2 = dx * dx + dy * dy
-    if L2 == 0.0:
-        t = np.zeros_like(xs)
-    else:
-        t = np.clip(((xs - x0) * dx + (ys - y0) * dy) / L2, 0.0, 1.0)
-    d2 = (xs - (x0 + t * dx)) ** 2 + (ys - (y0 + t * dy)) ** 2
-    canvas[ya:yb + 1, xa:xb + 1][d2 <= r * r] = 0
-
-
-def synth_stroke_image_u8(rs: np.random.RandomState) -> np.ndarray:
-    canvas = np.full((IMG_H, IMG_W), 255, np.uint8)
-    for _ in range(rs.randint(3, 13)):
-        npts = rs.randint(8, 41)
-        thick = float(rs.randint(2, 4))
-        x, y = rs.uniform(8, IMG_W - 8), rs.uniform(8, IMG_H - 8)
-        ang = rs.uniform(0, 2 * math.pi)
-        for _ in range(npts - 1):
-            ang += rs.normal(0.0, 0.6)
-            step = rs.uniform(2.0, 7.0)
-            nx = float(np.clip(x + step * math.cos(ang), 1, IMG_W - 2))
-            ny = float(np.clip(y + step * math.sin(ang), 1, IMG_H - 2))
-            _draw_segment(canvas, x, y, nx, ny, thick)
-            x, y = nx, ny
-    return canvas
-
-
-def synth_images(batch: int, seed: int = 1234) -> torch.Tensor:
-    """float32 [B,1,96,320] in [-1,1]; image i depends only on (seed, i)."""
-    out = np.empty((batch, 1, IMG_H, IMG_W), np.float32)
-    for i in range(batch):
-        rs = np.random.RandomState((seed * 1000003 + i) % (2 ** 31 - 1))
-        u8 = synth_stroke_image_u8(rs)
-        out[i, 0] = (u8.astype(np.float32) / 255.0 - 0.5) / 0.5
-    return torch.from_numpy(out)
-
-
-def synth_vocab(vocab_size: int):
-    """vocab / idx2char in the reference's ``vocab.json`` shape
-    (``/root/reference/app/src/utils.py:10-15``, specials first: ``src/config.py:43-47``)."""
-    toks = ["<pad>", "<sos>", "<eos>", "<unk>"] + [f"t{i}" for i in range(4, vocab_size)]
-    vocab = {t: i for i, t in enumerate(toks)}
-    idx2char = {i: t for i, t in enumerate(toks)}
-    return vocab, idx2char
+"""Synthetic checkpoint / stroke images / vocab (re-exported from the product's workload
+generator ``handwritten_math_ocr_api_b200.synthetic``: data definition, not arithmetic).
+TEST INFRASTRUCTURE ONLY."""
+from handwritten_math_ocr_api_b200.synthetic import (relative_position_index, state_dict_checksum,  # noqa: F401
+                                                     synth_images, synth_state_dict, synth_stroke_image_u8,
+                                                     synth_vocab)

@@ -10,8 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from handwritten_math_ocr_api_b200 import FormulaRecognitionModel  # noqa: E402
-from oracle.arch import ModelConfig  # noqa: E402
-from oracle.synth import synth_images, synth_state_dict  # noqa: E402
+from handwritten_math_ocr_api_b200.layout import ModelConfig  # noqa: E402
+from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)

@@ -12,8 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib  # noqa: E402
-from oracle.arch import ModelConfig  # noqa: E402
-from oracle.synth import synth_images, synth_state_dict  # noqa: E402
+from handwritten_math_ocr_api_b200.layout import ModelConfig  # noqa: E402
+from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict  # noqa: E402
 
 LAYER = ["wait qkv weights", "qkv gemm + kv append + sync", "self-attention (+dsmem stores)", "cluster barrier 1",
          "wait o weights", "out-proj gemm + dsmem stores", "cluster barrier 2", "layernorm 1 + sync",
