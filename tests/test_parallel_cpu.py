@@ -52,7 +52,7 @@ def _worker(rank, world, port, n_images, q):
         # ragged direct gather: rank r holds r+1 rows of r+2 columns
         mine = torch.full((rank + 1, rank + 2), rank + 10, dtype=torch.int64)
         rag = gather_tokens(mine, pad_id=0)
-        q.put((rank, full, rag))
+        q.put((rank, full.tolist(), rag.tolist()))       # plain lists: no shared-memory handles in the queue
     finally:
         dist.destroy_process_group()
 
@@ -68,6 +68,7 @@ def test_generate_sharded_world2_gloo(n_images):
     [p.join(60) for p in procs]
     single = _FakeModel().generate(torch.arange(n_images, dtype=torch.float32).reshape(n_images, 1))[0]
     for rank, full, rag in res:
+        full, rag = torch.tensor(full), torch.tensor(rag)
         assert full.shape[0] == n_images
         w = min(full.shape[1], single.shape[1])
         assert torch.equal(full[:, :w], single[:, :w])                     # N-GPU result == 1-GPU result
