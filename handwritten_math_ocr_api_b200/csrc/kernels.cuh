@@ -12,7 +12,9 @@ int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin
 int patch_embed(cudaStream_t st, const float* images, int B, const float* w, const float* b, const float* g,
                 const float* beta, float* x);
 int window_attention(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
-                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx);
+                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx);       // tensor-core (swin_attention.cu)
+int window_attention_fp32(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias,
+                          int B, int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx);   // CUDA-core reference
 
 // ---- decoder -------------------------------------------------------------------------------------
 struct DecodeState {      // device-resident control block of one generate call

@@ -1,0 +1,210 @@
+// Fused shifted-window attention on tensor cores (sm_100a).            swin_transformer.py:151-214,219-227
+//
+// One WARP = one (window, head) at a time, looping over windows with a fixed head so the head's
+// relative-position bias [49][49] stays in the warp's private shared memory.  Per item:
+//   * the cyclic shift, zero padding, window partition and their inverses are index arithmetic on
+//     the un-shifted, un-padded qkv buffer (rolled position (r,c) reads padded position
+//     ((r+sh)%Hp, (c+sw)%Wp)); a padded token has q = k = v = qkv.bias; its output is never written;
+//   * Q, K, V rows (49 x 32 bf16 each) are gathered with 16-byte cp.async into padded 64x40 tiles;
+//   * S = Q K^T (mma.sync m16n8k16, 4 m-tiles x 7 n-tiles x 2 k-steps), scaled by 32^-0.5, plus bias,
+//     plus the -100 region mask; softmax in fp32 registers with quad shuffles;
+//   * O = P V with P re-packed from the S accumulators straight into A fragments and V read through
+//     ldmatrix.trans; rows are normalised and scattered back to the original token order.
+// No block-level synchronisation at all: every warp owns its tiles (__syncwarp only).
+// 96.5 % of the encoder FLOPs are the tcgen05 GEMMs; this kernel's job is to stop the 49x49
+// attention + the roll/partition copies from costing more time than they do FLOPs.
+#include "kernels.cuh"
+
+namespace hmocr {
+namespace {
+
+constexpr int WS = 7, WN = 49, HD = 32;
+constexpr int TP = 40;            // tile pitch (bf16): 80-byte rows are conflict-free for ldmatrix
+constexpr int BP = 52;            // bias pitch (fp32)
+constexpr int WARPS = 4;
+
+struct WarpTile {
+  __nv_bfloat16 q[64][TP];
+  __nv_bfloat16 k[64][TP];
+  __nv_bfloat16 v[64][TP];
+  float bias[WN][BP];
+  int tok[64];       // token row in the qkv buffer, -1 if padded
+  int region[64];
+};
+
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2_trans(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                     const float* __restrict__ qkv_bias,
+                                                                     const float* __restrict__ rel_bias, int B, int H,
+                                                                     int W, int C, int heads, int sh, int sw, int Hp,
+                                                                     int Wp, __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpTile& s = reinterpret_cast<WarpTile*>(smem_raw)[warp];
+  const int gw = blockIdx.x * WARPS + warp;
+  const int per_head = (gridDim.x * WARPS) / heads;          // warps working on one head
+  if (per_head == 0 || gw >= per_head * heads) return;
+  const int h = gw % heads;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int nww = Wp / WS, nwin = (Hp / WS) * nww;
+  const int total = B * nwin;
+  const bool masked = (sh + sw) > 0;
+  const float scale = 0.17677669529663687f;                  // 32^-0.5 (swin_transformer.py:188)
+
+  // one-time: zero the padding rows (finite operands for the masked / zero-probability lanes) and
+  // fetch this head's relative-position bias
+  for (int i = lane; i < 15 * TP; i += 32) {
+    (&s.k[WN][0])[i] = __float2bfloat16(0.f);
+    (&s.v[WN][0])[i] = __float2bfloat16(0.f);
+    (&s.q[WN][0])[i] = __float2bfloat16(0.f);
+  }
+  for (int i = lane; i < WN * WN; i += 32) s.bias[i / WN][i % WN] = __ldg(rel_bias + (size_t)h * WN * WN + i);
+  __syncwarp();
+
+  for (int wi = gw / heads; wi < total; wi += per_head) {
+    const int b = wi / nwin, win = wi - b * nwin;
+    const int wr = win / nww, wc = win - wr * nww;
+    for (int p = lane; p < WN; p += 32) {
+      const int r = wr * WS + p / WS, c = wc * WS + p % WS;        // rolled, padded coordinates
+      const int pr = (r + sh) % Hp, pc = (c + sw) % Wp;            // padded coordinates before the roll
+      s.tok[p] = (pr < H && pc < W) ? (b * H + pr) * W + pc : -1;
+      int reg = 0;
+      if (masked) {
+        // slices (0,-7),(-7,-s),(-s,None) written in order; s == 0 makes the last one cover everything
+        const int hb = (sh == 0) ? 2 : ((r >= Hp - WS) + (r >= Hp - sh));
+        const int wb = (sw == 0) ? 2 : ((c >= Wp - WS) + (c >= Wp - sw));
+        reg = hb * 3 + wb;
+      }
+      s.region[p] = reg;
+    }
+    __syncwarp();
+    for (int i = lane; i < WN * 12; i += 32) {
+      const int p = i / 12, m = (i % 12) >> 2, ch = i & 3;
+      __nv_bfloat16* dst = (m == 0 ? &s.q[p][0] : (m == 1 ? &s.k[p][0] : &s.v[p][0])) + ch * 8;
+      const int col = m * C + h * HD + ch * 8;
+      const int tok = s.tok[p];
+      if (tok >= 0) {
+        cp_async16(dst, qkv + (size_t)tok * 3 * C + col);
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(qkv_bias + col));
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(qkv_bias + col + 4));
+        *reinterpret_cast<uint4*>(dst) =
+            make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c4.x, c4.y), pack_bf16(c4.z, c4.w));
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+      uint32_t aq[2][4];
+      ldsm4(smem_u32(&s.q[mt * 16 + (lane & 15)][(lane >> 4) * 8]), aq[0]);
+      ldsm4(smem_u32(&s.q[mt * 16 + (lane & 15)][(lane >> 4) * 8 + 16]), aq[1]);
+      const int r0 = mt * 16 + g4, r1 = r0 + 8;
+      const int rb0 = min(r0, WN - 1), rb1 = min(r1, WN - 1);       // clamp for the bias / region lookups
+      const int reg0 = s.region[rb0], reg1 = s.region[rb1];
+      float sc[7][4];
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t bk[2];
+        ldsm2(smem_u32(&s.k[nt * 8 + (lane & 7)][((lane >> 3) & 1) * 8]), bk);
+        mma16816(c, aq[0], bk);
+        ldsm2(smem_u32(&s.k[nt * 8 + (lane & 7)][((lane >> 3) & 1) * 8 + 16]), bk);
+        mma16816(c, aq[1], bk);
+        const int c0 = nt * 8 + 2 * t4;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = c0 + e;
+          float v0 = -INFINITY, v1 = -INFINITY;
+          if (col < WN) {
+            const int regc = s.region[col];
+            v0 = c[e] * scale + s.bias[rb0][col] + ((masked && regc != reg0) ? -100.0f : 0.0f);
+            v1 = c[2 + e] * scale + s.bias[rb1][col] + ((masked && regc != reg1) ? -100.0f : 0.0f);
+          }
+          sc[nt][e] = v0; sc[nt][2 + e] = v1;
+          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        const float p0 = __expf(sc[nt][0] - mx0), p1 = __expf(sc[nt][1] - mx0);
+        const float p2 = __expf(sc[nt][2] - mx1), p3 = __expf(sc[nt][3] - mx1);
+        sum0 += p0 + p1; sum1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2] = pack_bf16(p0, p1);        // row g4   , keys nt*8 + 2*t4 ..
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);    // row g4+8
+      }
+      pa[3][2] = 0u; pa[3][3] = 0u;                            // keys 56..63 do not exist
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+      const int tok0 = (r0 < WN) ? s.tok[r0] : -1, tok1 = (r1 < WN) ? s.tok[r1] : -1;
+#pragma unroll
+      for (int nt2 = 0; nt2 < 4; ++nt2) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t bv[2];
+          ldsm2_trans(smem_u32(&s.v[kk * 16 + (lane & 15)][nt2 * 8]), bv);
+          mma16816(o, pa[kk], bv);
+        }
+        const int col = h * HD + nt2 * 8 + 2 * t4;
+        if (tok0 >= 0) *reinterpret_cast<uint32_t*>(ctx + (size_t)tok0 * C + col) = pack_bf16(o[0] * inv0, o[1] * inv0);
+        if (tok1 >= 0) *reinterpret_cast<uint32_t*>(ctx + (size_t)tok1 * C + col) = pack_bf16(o[2] * inv1, o[3] * inv1);
+      }
+    }
+    __syncwarp();      // all lanes are done with the tiles before the next item overwrites them
+  }
+}
+
+}  // namespace
+
+int window_attention(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
+                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx) {
+  HM_CHECK(C == heads * HD, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
+  HM_CHECK(C % 8 == 0, "window_attention: C must be a multiple of 8");
+  const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;
+  const int sh = (Hp > WS) ? shift : 0, sw = (Wp > WS) ? shift : 0;   // swin_transformer.py:158-163
+  static bool attr = false;
+  const int smem = WARPS * (int)sizeof(WarpTile);
+  if (!attr) {
+    HM_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const long items = (long)B * (Hp / WS) * (Wp / WS) * heads;
+  int grid = 148 * 2;                                  // 2 CTAs per SM (104 KB each)
+  const int need = (int)((items + WARPS - 1) / WARPS);
+  if (need < grid) grid = need < 1 ? 1 : need;
+  if (grid * WARPS < heads) grid = ceil_div(heads, WARPS);
+  window_attn_mma_kernel<<<grid, WARPS * 32, smem, st>>>(qkv, qkv_bias, rel_bias, B, H, W, C, heads, sh, sw, Hp, Wp, ctx);
+  HM_LAUNCHED();
+  return 0;
+}
+
+}  // namespace hmocr

@@ -287,7 +287,8 @@ int patch_embed(cudaStream_t st, const float* images, int B, const float* w, con
   return 0;
 }
 
-int window_attention(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
+// CUDA-core fp32 version (round-1 first path); kept as an independent implementation for A/B tests.
+int window_attention_fp32(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
                      int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx) {
   HM_CHECK(C == heads * HD, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   HM_CHECK(heads % HC == 0, "window_attention: heads=%d must be a multiple of %d", heads, HC);
