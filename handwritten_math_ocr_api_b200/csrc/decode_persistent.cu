@@ -56,7 +56,9 @@ struct Smem {
   alignas(16) float fcb[DP_FCB_MAX];       // this CTA's slice of fc_out.bias
   alignas(8) uint64_t full[NSLOT];
   alignas(8) uint64_t fpbar[2];
+  alignas(8) uint64_t xbar[4];             // exchange barriers (st.async mode): context, y32, hidden, partials
 };
+enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3 };
 static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs must fit one SM");
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -82,6 +84,45 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+// st.async: a remote (DSMEM) store that also performs complete_tx(bytes) on an mbarrier of the
+// destination CTA - the sender needs no fence and no barrier, the receiver waits on its own mbarrier.
+__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v),
+               "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t a, uint32_t b, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr),
+               "r"(a), "r"(b), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar)
+               : "memory");
+}
+// wait for a phase whose bytes were written by other CTAs of the cluster (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) {
+      printf("hmocr: exchange mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -254,7 +295,10 @@ __device__ __forceinline__ void update_partial(Partial& a, float v, int idx) {
 
 struct LnRegs { float4 g0, g1, b0, b1; };
 
-template <int NI>
+// ASYNC = true : exchanges use st.async + per-buffer mbarriers (point-to-point: a CTA proceeds as soon
+//                as ITS inputs have arrived; no fence, no cluster-wide barrier)
+// ASYNC = false: plain st.shared::cluster + barrier.cluster (first implementation, kept for A/B tests)
+template <int NI, bool ASYNC>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -710,8 +754,8 @@ int g_max_clusters = 0;
 int decode_persistent_init() {
   static bool done = false;
   if (done) return 0;
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL * 64);
   cfg.blockDim = dim3(THREADS);
@@ -720,7 +764,7 @@ int decode_persistent_init() {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<20>, &cfg));
+  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<20, false>, &cfg));
   HM_CHECK(g_max_clusters >= 1, "device cannot host an 8-CTA decode cluster");
   done = true;
   return 0;
@@ -749,9 +793,9 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   p.rows_per_cluster = rpc;
   dim3 grid(ceil_div(p.rows, rpc) * CL);
   if (p.tmax <= 160)
-    decode_persistent_kernel<20><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    decode_persistent_kernel<20, false><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
   else
-    decode_persistent_kernel<32><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    decode_persistent_kernel<32, false><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
   HM_LAUNCHED();
   return 0;
 }
