@@ -79,10 +79,9 @@ struct hmocr_engine {
   Lin ca_kv;                          // stacked cross-attention K/V projection of all layers [L*2d, d]
   Lin fc;
   // packed operands of the persistent cluster decode kernel (decode_persistent.cuh)
-  uint8_t *dp_wblob = nullptr, *dp_fcblob = nullptr;
+  uint8_t* dp_wstream = nullptr;
   float *dp_fparams = nullptr, *dp_fcbias = nullptr, *dp_lnparams = nullptr;
-  int rows_per_cluster = 0;           // 0 = automatic
-  int dp_fc_chunks = 0;
+  int dp_fc_tiles = 0, dp_chunks_per_step = 0;
   int decode_impl = 0;                // 0 = persistent cluster kernel, 1 = per-kernel step graph
   int steps_per_launch = 16;
   int trace_step = -1;                // >= 0: record phase-boundary clocks of that decode step
@@ -454,11 +453,13 @@ int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B
 // ------------------------------------------------------------------------------------------------
 // operand packing for decode_persistent.cu (host side, once at load)
 // ------------------------------------------------------------------------------------------------
-void pack_rows(std::vector<__nv_bfloat16>& dst, size_t off, const float* w, int row0, int nrows, int K, int valid_rows) {
-  for (int r = 0; r < nrows; ++r)
-    for (int k = 0; k < K + 8; ++k) {
-      const bool ok = (k < K) && (row0 + r < valid_rows);
-      dst[off + (size_t)r * (K + 8) + k] = __float2bfloat16(ok ? w[(size_t)(row0 + r) * K + k] : 0.f);
+// 16 weight rows [row0, row0+16) x 256 input columns [col0, col0+256) of a [valid_rows, K] fp32 matrix -> one
+// stream chunk (bf16 [16][264], zero padded)
+void pack_chunk(std::vector<__nv_bfloat16>& dst, size_t off, const float* w, int row0, int col0, int K, int valid_rows) {
+  for (int r = 0; r < DP_CH_ROWS; ++r)
+    for (int k = 0; k < 264; ++k) {
+      const bool ok = (k < 256) && (row0 + r < valid_rows);
+      dst[off + (size_t)r * 264 + k] = __float2bfloat16(ok ? w[(size_t)(row0 + r) * K + col0 + k] : 0.f);
     }
 }
 
@@ -468,7 +469,11 @@ int pack_decode_operands(hmocr_engine* e) {
   HM_CHECK(d == 256 && ff == 512 && c.nhead == 8,
            "the persistent decode kernel is specialised for d_model=256, nhead=8, dim_feedforward=512 "
            "(reference config.py:19-21); got %d/%d/%d", d, c.nhead, ff);
-  std::vector<__nv_bfloat16> blob((size_t)L * 8 * DP_LAYER_CTA_BYTES / 2);
+  HM_CHECK(V <= 8 * DP_FCB_MAX, "vocab_size %d exceeds the persistent decode kernel's limit %d", V, 8 * DP_FCB_MAX);
+  e->dp_fc_tiles = ((V + 127) / 128 + 7) / 8 * 8;      // 16-row tiles per CTA, a multiple of the 8 warps
+  e->dp_chunks_per_step = DP_LAYER_CHUNKS * L + e->dp_fc_tiles;
+  const size_t S = (size_t)e->dp_chunks_per_step, CE = DP_CHUNK / 2;        // chunk size in elements
+  std::vector<__nv_bfloat16> stream(8 * S * CE);
   std::vector<float> fpar((size_t)L * 8 * DP_FPC), lnpar((size_t)L * 6 * d);
   for (int l = 0; l < L; ++l) {
     const std::string p = "decoder.decoder.layers." + std::to_string(l) + ".";
@@ -486,16 +491,15 @@ int pack_decode_operands(hmocr_engine* e) {
     HM_TRY(need(e, p + "linear2.weight", {d, ff}, &w2));
     HM_TRY(need(e, p + "linear2.bias", {d}, &b2));
     for (int ct = 0; ct < 8; ++ct) {
-      size_t off = ((size_t)l * 8 + ct) * (DP_LAYER_CTA_BYTES / 2);
-      for (int part = 0; part < 3; ++part) {           // q, k, v rows of head ct
-        pack_rows(blob, off, sin->f.data(), part * d + ct * 32, 32, d, 3 * d);
-        off += DP_CHUNK / 2;
-      }
-      pack_rows(blob, off, so->f.data(), ct * 32, 32, d, d); off += DP_CHUNK / 2;
-      pack_rows(blob, off, cin->f.data(), ct * 32, 32, d, 3 * d); off += DP_CHUNK / 2;
-      pack_rows(blob, off, co->f.data(), ct * 32, 32, d, d); off += DP_CHUNK / 2;
-      pack_rows(blob, off, w1->f.data(), ct * 64, 64, d, ff); off += DP_CHUNK;
-      pack_rows(blob, off, w2->f.data(), ct * 32, 32, ff, d);
+      size_t off = ((size_t)ct * S + (size_t)l * DP_LAYER_CHUNKS) * CE;
+      for (int part = 0; part < 3; ++part)             // q, k, v rows of head ct
+        for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, sin->f.data(), part * d + ct * 32 + 16 * m, 0, d, 3 * d);
+      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, so->f.data(), ct * 32 + 16 * m, 0, d, d);
+      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, cin->f.data(), ct * 32 + 16 * m, 0, d, 3 * d);
+      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, co->f.data(), ct * 32 + 16 * m, 0, d, d);
+      for (int m = 0; m < 4; ++m, off += CE) pack_chunk(stream, off, w1->f.data(), ct * 64 + 16 * m, 0, d, ff);
+      for (int m = 0; m < 2; ++m)
+        for (int kh = 0; kh < 2; ++kh, off += CE) pack_chunk(stream, off, w2->f.data(), ct * 32 + 16 * m, 256 * kh, ff, d);
     }
     const char* ln[3] = {"norm1", "norm2", "norm3"};
     for (int i = 0; i < 3; ++i) {
@@ -516,28 +520,22 @@ int pack_decode_operands(hmocr_engine* e) {
       memcpy(fp + DPC_B2, b2->f.data() + ct * 32, sizeof(float) * 32);
     }
   }
-  HM_CHECK(V <= 8 * DP_FCB_MAX, "vocab_size %d exceeds the persistent decode kernel's limit %d", V, 8 * DP_FCB_MAX);
-  e->dp_fc_chunks = 2 * ((V + 511) / 512);      // 32-row chunks, consumed two per phase
-  const int cols_per_cta = e->dp_fc_chunks * 32;
-  std::vector<__nv_bfloat16> fcb((size_t)8 * e->dp_fc_chunks * DP_CHUNK / 2);
+  const int cols_per_cta = e->dp_fc_tiles * 16;
   std::vector<float> fcbias((size_t)8 * cols_per_cta, 0.f);
   {
     const HostTensor *w, *b;
     HM_TRY(need(e, "decoder.fc_out.weight", {V, d}, &w));
     HM_TRY(need(e, "decoder.fc_out.bias", {V}, &b));
     for (int ct = 0; ct < 8; ++ct)
-      for (int j = 0; j < e->dp_fc_chunks; ++j)
-        pack_rows(fcb, ((size_t)ct * e->dp_fc_chunks + j) * (DP_CHUNK / 2), w->f.data(), ct * cols_per_cta + j * 32, 32,
-                  d, V);
+      for (int m = 0; m < e->dp_fc_tiles; ++m)
+        pack_chunk(stream, ((size_t)ct * S + (size_t)L * DP_LAYER_CHUNKS + m) * CE, w->f.data(), ct * cols_per_cta + 16 * m,
+                   0, d, V);
     memcpy(fcbias.data(), b->f.data(), sizeof(float) * V);
   }
   void* q;
-  HM_TRY(arena_alloc(e, blob.size() * 2, &q));
-  HM_CUDA(cudaMemcpy(q, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice));
-  e->dp_wblob = static_cast<uint8_t*>(q);
-  HM_TRY(arena_alloc(e, fcb.size() * 2, &q));
-  HM_CUDA(cudaMemcpy(q, fcb.data(), fcb.size() * 2, cudaMemcpyHostToDevice));
-  e->dp_fcblob = static_cast<uint8_t*>(q);
+  HM_TRY(arena_alloc(e, stream.size() * 2, &q));
+  HM_CUDA(cudaMemcpy(q, stream.data(), stream.size() * 2, cudaMemcpyHostToDevice));
+  e->dp_wstream = static_cast<uint8_t*>(q);
   HM_TRY(upload_f32(e, fpar.data(), fpar.size(), &e->dp_fparams));
   HM_TRY(upload_f32(e, lnpar.data(), lnpar.size(), &e->dp_lnparams));
   HM_TRY(upload_f32(e, fcbias.data(), fcbias.size(), &e->dp_fcbias));
@@ -566,11 +564,12 @@ int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int 
   HM_TRY(repack_memkv(st, memkv, B, L, memk, memv));
   HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   DecPersistParams p;
-  p.wblob = e->dp_wblob; p.fcblob = e->dp_fcblob; p.fparams = e->dp_fparams; p.fc_bias = e->dp_fcbias;
-  p.lnparams = e->dp_lnparams; p.rows_per_cluster = e->rows_per_cluster;
+  p.wstream = e->dp_wstream; p.fparams = e->dp_fparams; p.fc_bias = e->dp_fcbias;
+  p.lnparams = e->dp_lnparams;
   p.emb = e->emb; p.pos = e->pos; p.kcache = kcache; p.vcache = vcache; p.memk = memk; p.memv = memv;
   p.tokens = tokens; p.logprob = logprob; p.finished = finished; p.state = state;
-  p.rows = rows; p.images = B; p.beam = 1; p.num_layers = L; p.fc_chunks = e->dp_fc_chunks;
+  p.rows = rows; p.images = B; p.beam = 1; p.num_layers = L; p.fc_tiles = e->dp_fc_tiles;
+  p.chunks_per_step = e->dp_chunks_per_step;
   p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
   p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id;
   p.trace = nullptr; p.trace_step = e->trace_step;
@@ -702,7 +701,7 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   size_t total = 0;
   for (auto& kv : e->host) total += kv.second.f.size() * 4 + 1024;
   e->arena_cap = total + (size_t)e->vpad * d * 4 + (size_t)c.num_layers * 2 * d * (d + 1) * 4 + (64u << 20) +
-                 (size_t)c.num_layers * 8 * DP_LAYER_CTA_BYTES + (size_t)(V / 512 + 1) * 8 * 2 * DP_CHUNK + (size_t)c.num_layers * DP_FP_LAYER * 4;
+                 (size_t)8 * (DP_LAYER_CHUNKS * c.num_layers + V / 128 + 16) * DP_CHUNK + (size_t)c.num_layers * 8192 * 4;
   HM_CUDA(cudaMalloc(&e->arena, e->arena_cap));
   e->arena_used = 0;
 
@@ -802,9 +801,6 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
   } else if (n == "steps_per_launch") {
     HM_CHECK(value >= 1 && value <= 256, "steps_per_launch must be in [1,256]");
     e->steps_per_launch = value;
-  } else if (n == "rows_per_cluster") {
-    HM_CHECK(value >= 0 && value <= 16, "rows_per_cluster must be in [0,16] (0 = automatic)");
-    e->rows_per_cluster = value;
   } else if (n == "trace_step") {
     e->trace_step = value;
   } else {

@@ -1,6 +1,5 @@
 """Decode/encoder time of one generate() call as a function of the batch (latency- vs throughput-bound check).
 
-    python profiles/sweep_batch.py [--batches 64,128,256,512] [--max-len 150] [--rpc 0]
 """
 import argparse
 import os
@@ -16,13 +15,10 @@ from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_di
 ap = argparse.ArgumentParser()
 ap.add_argument("--batches", default="64,128,256,512")
 ap.add_argument("--max-len", type=int, default=150)
-ap.add_argument("--rpc", type=int, default=0)
 a = ap.parse_args()
 cfg = ModelConfig()
 m = FormulaRecognitionModel(cfg.vocab_size)
 m.load_state_dict(synth_state_dict(cfg, seed=0, eos_bias_sigma=0.0))
-if a.rpc:
-    m.set_option("rows_per_cluster", a.rpc)
 base = synth_images(8, seed=1234).cuda()
 for B in [int(x) for x in a.batches.split(",")]:
     imgs = base.repeat((B + 7) // 8, 1, 1, 1)[:B].contiguous()
@@ -35,5 +31,5 @@ for B in [int(x) for x in a.batches.split(",")]:
         e, d = m.last_timings_ms()
         enc.append(e); dec.append(d)
     e, d = min(enc), min(dec)
-    print(f"B={B:4d} rpc={a.rpc}: encoder {e:7.3f} ms  decode {d:7.3f} ms  ({d / a.max_len * 1e3:6.1f} us/step)  "
+    print(f"B={B:4d}: encoder {e:7.3f} ms  decode {d:7.3f} ms  ({d / a.max_len * 1e3:6.1f} us/step)  "
           f"{B / (e + d) * 1e3:8.1f} img/s", flush=True)

@@ -15,17 +15,14 @@ from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib  # noqa:
 from handwritten_math_ocr_api_b200.layout import ModelConfig  # noqa: E402
 from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict  # noqa: E402
 
-LAYER = ["wait qkv weights", "qkv gemm + kv append + sync", "self-attention (+dsmem stores)", "cluster barrier 1",
-         "wait o weights", "out-proj gemm + dsmem stores", "cluster barrier 2", "layernorm 1 + sync",
-         "wait cq weights", "cross-q gemm + sync", "cross-attention (+dsmem stores)", "cluster barrier 3",
-         "wait co weights", "out-proj gemm + dsmem stores", "cluster barrier 4", "layernorm 2 + sync",
-         "wait f1 weights", "linear1 gemm + dsmem stores", "cluster barrier 5", "wait f2 weights",
-         "linear2 gemm + dsmem stores", "cluster barrier 6", "layernorm 3 + sync"]
-TAIL = ["fc_out slices (all chunks) + warp/block reduce + dsmem", "cluster barrier 7", "token select + outputs + sync",
-        "embed next token + sync"]
+LAYER = ["qkv tiles + sync", "self-attention + context send", "wait context 1", "out-proj 1 tiles + y send", "wait y 1",
+         "layernorm 1 + sync", "cross-q tiles + sync", "cross-attention + context send", "wait context 2",
+         "out-proj 2 tiles + y send", "wait y 2", "layernorm 2 + sync", "linear1 tiles + hidden send", "wait hidden",
+         "linear2 tiles + y send", "wait y 3", "layernorm 3 + sync", "next layer: bias wait"]
+TAIL = ["fc_out tiles + warp reduce + sync", "partials send + wait", "token select + embed next + sync"]
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--batch", type=int, default=240)
+ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--step", type=int, default=100)
 a = ap.parse_args()
 cfg = ModelConfig()
@@ -41,7 +38,7 @@ torch.cuda.synchronize()
 buf = (C.c_int64 * 1024)()
 _lib.check(_lib.load().hmocr_read_trace(m._eng.handle, buf, 1024), "read_trace")
 st = [x for x in buf if x != 0]
-n_layer = len(LAYER) + 1
+n_layer = len(LAYER)
 L = cfg.num_layers
 d = [st[i + 1] - st[i] for i in range(len(st) - 1)]
 clk = 1.965e3    # cycles per us at max clock (approximate)
