@@ -28,13 +28,19 @@
 // inputs have arrived.  Six exchanges per layer (context, y, context, y, hidden, y) + one per step
 // (arg-max partials).  barrier.cluster is used only at kernel start and end.
 //
-// Attention.  One warp per (row, head): two passes over the bf16 K then V history with a rolling
-// register pipeline (next 4 key blocks in flight while the current 4 are consumed), 512-byte
-// coalesced warp loads; this step's own key/value come from shared memory.  The cache rows of the
-// NEXT layer are pulled into L2 (cp.async.bulk.prefetch.L2) one layer ahead.
+// Attention.  One warp per (row, head), on tensor cores: S = K q as mma.m16n8k16 with 16 cached keys
+// as the M operand (fp16 K cache [key][32], fragments loaded straight from global memory, 64 B per
+// key), softmax in fp32, then O = V^T p with 16 head dims as the M operand (fp16 V cache stored
+// TRANSPOSED, [dim][key], so its fragments are also plain 16-byte global loads); probabilities pass
+// through a 512-byte per-warp shared buffer.  ~45 instructions per 32 keys instead of ~200 on CUDA
+// cores; two 32-key blocks of K and of V are in flight per warp.  The caches are fp16 (not bf16): same
+// bytes, 3 more mantissa bits.  The cache rows of the NEXT layer are pulled into L2
+// (cp.async.bulk.prefetch.L2) one layer ahead.
 //
 // Occupancy is part of the design: 106 KB of shared memory and <= 128 registers, so TWO CTAs (of
 // different clusters) share an SM; B=256 runs as 32 clusters in a single wave.
+#include <cuda_fp16.h>
+
 #include "decode_persistent.cuh"
 
 namespace hmocr {
@@ -43,7 +49,7 @@ namespace {
 constexpr int CL = 8, THREADS = 256, NW = 8, R = DP_ROWS;
 constexpr int D = 256, FF = 512, HD = 32, NH = 8, MEM_S = 30;
 constexpr int PD = D + 8, PF = FF + 8;            // padded operand pitches (elements): conflict-free ldmatrix
-constexpr float ATT_SCALE = 0.17677669529663687f;
+constexpr float ATT_SCALE = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32): softmax on ex2
 constexpr float LN_EPS = 1e-5f;
 
 struct __align__(16) Partial { float m; int idx; float s; int pad; };
@@ -56,9 +62,10 @@ struct Smem {
   alignas(16) __nv_bfloat16 hf[R][PF];      // relu(linear1) gathered from the 8 slices
   alignas(16) float stg[4][16][9];          // staging of GEMM tiles [task][feature][row] (hidden: bf16 [8][72])
   alignas(16) float x32s[R][32];            // fp32 residual stream, this CTA's 32-feature slice only
-  alignas(16) float qs[R][HD];              // this head's scaled query
-  alignas(16) __nv_bfloat16 knew[R][HD];    // this step's key / value of head c
-  alignas(16) __nv_bfloat16 vnew[R][HD];
+  alignas(16) __half qh[R][HD];             // this head's scaled query (fp16 mma operand)
+  alignas(16) uint32_t pbuf[NW][128];       // per-warp softmax probabilities in P-operand order (half2 words)
+  alignas(16) __half knew[R][HD];           // this step's key / value of head c (appended to the caches after use)
+  alignas(16) __half vnew[R][HD];
   Partial part[CL][R];                      // per-CTA argmax / sum-exp partials (gathered)
   Partial wpart[NW][R];                     // per-warp partials
   alignas(16) float fpar[2][DP_FPC];        // this CTA's bias slices of layer l / l+1
@@ -97,7 +104,9 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mba
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar)
                : "memory");
 }
-// wait for a phase whose bytes were written by other CTAs of the cluster (acquire at cluster scope)
+// Wait for a phase whose bytes were written into THIS CTA's shared memory by st.async of other CTAs.
+// Plain try_wait, as for TMA multicast: a cluster-scope acquire would make ptxas emit CCTL.IVALL (an
+// L1 invalidate, ~400 cycles) after every wait, and shared memory is not cached in L1.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   long long t0 = 0;
@@ -105,7 +114,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
         : "r"(a), "r"(parity)
@@ -164,107 +173,158 @@ __device__ __forceinline__ void gemm16(const uint8_t* W, const __nv_bfloat16* X,
   for (int i = 0; i < 4; ++i) c[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
 }
 
-__device__ __forceinline__ float dot8(const float (&q)[8], const uint4 u) {
-  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-  float s = q[0] * a.x;
-  s = fmaf(q[1], a.y, s); s = fmaf(q[2], b.x, s); s = fmaf(q[3], b.y, s);
-  s = fmaf(q[4], c.x, s); s = fmaf(q[5], c.y, s); s = fmaf(q[6], d.x, s); s = fmaf(q[7], d.y, s);
-  return s;
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4 u) {
-  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-  acc[0] = fmaf(p, a.x, acc[0]); acc[1] = fmaf(p, a.y, acc[1]); acc[2] = fmaf(p, b.x, acc[2]);
-  acc[3] = fmaf(p, b.y, acc[3]); acc[4] = fmaf(p, c.x, acc[4]); acc[5] = fmaf(p, c.y, acc[5]);
-  acc[6] = fmaf(p, d.x, acc[6]); acc[7] = fmaf(p, d.y, acc[7]);
-}
-__device__ __forceinline__ float group_dot(const float (&q)[8], const uint4 u) {   // sum over the 4 dim chunks
-  float a = dot8(q, u);
-  a += __shfl_xor_sync(0xffffffffu, a, 1);
-  a += __shfl_xor_sync(0xffffffffu, a, 2);
-  return a;
+__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-// One query row of one head against `nhist` cached keys (global, bf16 [key][32]) plus, if `knew` is
-// given, this step's own key/value (shared memory).  Lane = (key group jg = lane/4, dim chunk dc =
-// lane%4): every load instruction of the warp fetches 8 consecutive 64-byte rows = 512 contiguous
-// bytes.  Keys are processed in batches of 4 blocks (32 keys); the next batch is in flight while the
-// current one is consumed, first for K (scores kept in registers), then for V.
-// Result: out[8] = the context of dims dc*8 .. dc*8+7, identical in the 8 lanes that share dc.
-template <int NB>
-__device__ __forceinline__ void attend(const float* q, const __nv_bfloat16* Kc, const __nv_bfloat16* Vc, int nhist,
-                                       const __nv_bfloat16* knew, const __nv_bfloat16* vnew, int lane,
-                                       float (&out)[8]) {
-  const int jg = lane >> 2, dc = lane & 3;
-  float qv[8];
-  {
-    const float4 a = *reinterpret_cast<const float4*>(q + dc * 8), b = *reinterpret_cast<const float4*>(q + dc * 8 + 4);
-    qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
-  }
-  const int niter = (nhist + 7) >> 3;
-  float sc[NB * 4];
-  uint4 buf[2][4];
-  auto load4 = [&](const __nv_bfloat16* base, int b, uint4 (&dst)[4]) {
+// ---- fragment-major K / V caches ---------------------------------------------------------------------
+// Both caches are stored in the register layout of the mma.m16n8k16 A operand, so a cache fragment is ONE
+// coalesced 16-byte load per lane (512 contiguous bytes per warp instruction) and needs no address
+// arithmetic, no clamping and no register shuffling.  A block = 32 keys x 32 dims = 2048 bytes:
+//   K block: [tile 0..1][k-step s 0..1][lane][a0 a1 a2 a3]   tile = 16 keys, lane = (g, t):
+//            a0 = key g,   dims 16s+4t+{0,1};  a1 = key g+8, same dims;
+//            a2 = key g,   dims 16s+4t+{2,3};  a3 = key g+8, same dims.
+//   V block: [k-step ks 0..1][m-tile mt 0..1][lane][a0 a1 a2 a3]   k-step = the 16 keys of K tile ks:
+//            a0 = dim 4g+2mt,   slots 2t, 2t+1;   a1 = dim 4g+2mt+1, same slots;
+//            a2 = dim 4g+2mt,   slots 2t+8, 2t+9; a3 = dim 4g+2mt+1, same slots,
+//            where key r = g' + 8h of the tile sits in slot 8*(g'/4) + 2*(g'%4) + h - so the two scores a
+//            lane gets from the K tile (keys g', g'+8) are exactly one packed half2 of the P operand.
+// Offsets below are in halves, relative to the start of the (layer, row, head) region.
+__device__ __forceinline__ int kfrag_word(int key_in_blk, int i) {     // 32-bit word index of dims (2i, 2i+1), i < 16
+  const int tile = key_in_blk >> 4, r = key_in_blk & 15, g = r & 7, h = r >> 3;
+  const int sidx = i >> 3, t = (i >> 1) & 3, w = i & 1;
+  return tile * 256 + sidx * 128 + (g * 4 + t) * 4 + 2 * w + h;
+}
+__device__ __forceinline__ int vfrag_half(int key_in_blk, int d) {      // half index of (dim d, key)
+  const int ks = key_in_blk >> 4, r = key_in_blk & 15, g = r & 7, h = r >> 3;
+  const int gd = d >> 2, mt = (d >> 1) & 1, hd = d & 1;
+  return (ks * 2 + mt) * 256 + (gd * 4 + (g & 3)) * 8 + (2 * (g >> 2) + hd) * 2 + h;
+}
+
+// One query row of one head against n cached keys, on tensor cores.
+//   scores:  S[16 keys x 8] = K[16 keys x 32 dims] . q      (q replicated in all 8 columns; two k-steps)
+//   output:  O[16 dims x 8] = Vt[16 dims x 16 keys] . p     (p replicated in all columns; two m-tiles)
+// q is pre-scaled by log2(e)/sqrt(32): the softmax runs on ex2.  Probabilities go through a 64-byte per
+// block shared buffer in P-operand order.  Keys come in blocks of 32; two blocks of K and of V are in flight.
+// Result: out[j] = context of dim 4*g4 + j (identical in the 4 lanes that share g4).
+// If NEW, one more key/value (this step's own, still in shared memory) is folded in on CUDA cores, so the
+// attention never waits for its own cache append to travel through L2.
+template <int NB, bool NEW>
+__device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, const __half* Vc, int n,
+                                           const __half* knew, const __half* vnew, uint32_t* pbuf, int lane,
+                                           float (&out)[4], long long* tr) {
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const uint2 q0 = *reinterpret_cast<const uint2*>(qh + 4 * t4), q1 = *reinterpret_cast<const uint2*>(qh + 16 + 4 * t4);
+  const int nb = (n + 31) >> 5;
+  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;       // + 128 * block + 32 * fragment
+  const uint4* Vl = reinterpret_cast<const uint4*>(Vc) + lane;
+  uint4 kr[2][4], vr[2][4];
+  auto load4 = [&](const uint4* base, int b, uint4 (&d)[4]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = min(jg + 8 * (4 * b + u), nhist - 1);          // clamped: always a valid row, masked below
-      dst[u] = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)j * HD + dc * 8));
-    }
+    for (int u = 0; u < 4; ++u) d[u] = __ldcg(base + 128 * b + 32 * u);
   };
-  if (niter > 0) load4(Kc, 0, buf[0]);
+  if (0 < nb) load4(Kl, 0, kr[0]);
+  if (NB > 1 && 1 < nb) load4(Kl, 1, kr[1]);
+  if (0 < nb) load4(Vl, 0, vr[0]);
+  if (NB > 1 && 1 < nb) load4(Vl, 1, vr[1]);
+  float snew = -INFINITY;
+  if (NEW) {
+    const uint4 kn = *reinterpret_cast<const uint4*>(knew + t4 * 8), qn = *reinterpret_cast<const uint4*>(qh + t4 * 8);
+    const uint32_t qw[4] = {qn.x, qn.y, qn.z, qn.w}, kw[4] = {kn.x, kn.y, kn.z, kn.w};
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[i]));
+      const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&kw[i]));
+      a = fmaf(qf.x, kf.x, a); a = fmaf(qf.y, kf.y, a);
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    snew = a;
+  }
+  float sc[NB * 4];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    if (b + 1 < NB && (b + 1) * 4 < niter) load4(Kc, b + 1, buf[(b + 1) & 1]);
-    if (b * 4 < niter) {                                            // warp-uniform
+    if (b < nb) {                                                   // warp-uniform
+      const uint4(&d)[4] = kr[b & 1];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float a = group_dot(qv, buf[b & 1][u]);
-        sc[4 * b + u] = (jg + 8 * (4 * b + u) < nhist) ? a : -INFINITY;
+      for (int tile = 0; tile < 2; ++tile) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(c, d[2 * tile].x, d[2 * tile].y, d[2 * tile].z, d[2 * tile].w, q0.x, q0.y);
+        mma_f16(c, d[2 * tile + 1].x, d[2 * tile + 1].y, d[2 * tile + 1].z, d[2 * tile + 1].w, q1.x, q1.y);
+        const int key = 32 * b + 16 * tile + g4;
+        sc[4 * b + 2 * tile] = (key < n) ? c[0] : -INFINITY;
+        sc[4 * b + 2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
       }
+      if (b + 2 < NB && b + 2 < nb) load4(Kl, b + 2, kr[b & 1]);
     } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) sc[4 * b + u] = -INFINITY;
     }
   }
-  if (niter > 0) load4(Vc, 0, buf[0]);                              // first V batch flies during the softmax
-  float m = -INFINITY, snew = -INFINITY;
-  uint4 vn = make_uint4(0u, 0u, 0u, 0u);
-  if (knew != nullptr) {
-    snew = group_dot(qv, *reinterpret_cast<const uint4*>(knew + dc * 8));
-    vn = *reinterpret_cast<const uint4*>(vnew + dc * 8);
-    m = snew;
-  }
+  if (tr) tr[0] = clock64();
+  float m = snew;
 #pragma unroll
   for (int i = 0; i < NB * 4; ++i) m = fmaxf(m, sc[i]);
 #pragma unroll
   for (int o = 4; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   float den = 0.f;
-#pragma unroll
-  for (int i = 0; i < NB * 4; ++i) { sc[i] = __expf(sc[i] - m); den += sc[i]; }
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  uint32_t* pw = pbuf + (g4 & 3) * 2 + (g4 >> 2);                   // this lane's word of each 8-word k-step
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    if (b + 1 < NB && (b + 1) * 4 < niter) load4(Vc, b + 1, buf[(b + 1) & 1]);
-    if (b * 4 < niter) {
+    if (b < nb) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) axpy8(acc, sc[4 * b + u], buf[b & 1][u]);
+      for (int tile = 0; tile < 2; ++tile) {
+        const __half2 ph = __floats2half2_rn(ex2f(sc[4 * b + 2 * tile] - m), ex2f(sc[4 * b + 2 * tile + 1] - m));
+        const float2 pf = __half22float2(ph);                       // normalise with the rounded weights
+        den += pf.x + pf.y;
+        if (t4 == 0) pw[16 * b + 8 * tile] = *reinterpret_cast<const uint32_t*>(&ph);
+      }
+    }
+  }
+  __syncwarp();
+  if (tr) tr[1] = clock64();
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (b < nb) {
+      const uint4(&d)[4] = vr[b & 1];
+      const uint2 p0 = *reinterpret_cast<const uint2*>(pbuf + 16 * b + 2 * t4);
+      const uint2 p1 = *reinterpret_cast<const uint2*>(pbuf + 16 * b + 8 + 2 * t4);
+      mma_f16(acc0, d[0].x, d[0].y, d[0].z, d[0].w, p0.x, p0.y);
+      mma_f16(acc1, d[1].x, d[1].y, d[1].z, d[1].w, p0.x, p0.y);
+      mma_f16(acc0, d[2].x, d[2].y, d[2].z, d[2].w, p1.x, p1.y);
+      mma_f16(acc1, d[3].x, d[3].y, d[3].z, d[3].w, p1.x, p1.y);
+      if (b + 2 < NB && b + 2 < nb) load4(Vl, b + 2, vr[b & 1]);
     }
   }
 #pragma unroll
-  for (int o = 4; o < 32; o <<= 1) {
-    den += __shfl_xor_sync(0xffffffffu, den, o);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-  }
-  if (knew != nullptr) {
-    const float pn = __expf(snew - m);
+  for (int o = 4; o < 32; o <<= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  if (tr) tr[2] = clock64();
+  if (NEW) {
+    const float pn = __half2float(__float2half_rn(ex2f(snew - m)));
     den += pn;
-    axpy8(acc, pn, vn);
+    const uint2 vn = *reinterpret_cast<const uint2*>(vnew + 4 * g4);
+    const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&vn.x));
+    const float2 v23 = __half22float2(*reinterpret_cast<const __half2*>(&vn.y));
+    acc0[0] = fmaf(pn, v01.x, acc0[0]); acc0[2] = fmaf(pn, v01.y, acc0[2]);
+    acc1[0] = fmaf(pn, v23.x, acc1[0]); acc1[2] = fmaf(pn, v23.y, acc1[2]);
   }
-  const float inv = 1.0f / den;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = acc[e] * inv;
+  const float inv = __fdividef(1.0f, den);
+  out[0] = acc0[0] * inv; out[1] = acc0[2] * inv; out[2] = acc1[0] * inv; out[3] = acc1[2] * inv;
+  __syncwarp();                                                     // pbuf may be rewritten by the next call
 }
 
 __device__ __forceinline__ void merge_partial(Partial& a, const Partial& b) {
@@ -328,12 +388,13 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       bulk_g2s(s.slot[warp], wst + (size_t)wpos * DP_CHUNK, DP_CHUNK, &s.full[warp]);
     }
   };
-  auto slot_wait = [&]() { mbar_wait(&s.full[warp], wk & 1); };
+  const bool dbg_noweights = (p.flags & 4) != 0;      // timing experiments only (results are wrong)
+  auto slot_wait = [&]() { if (!dbg_noweights || wk == 0) mbar_wait(&s.full[warp], wk & 1); };
   auto slot_release = [&]() {
     __syncwarp();
     ++wk; wgi += NW; wpos += NW;
     if (wpos >= S) wpos -= S;
-    if (lane == 0) slot_fetch();
+    if (lane == 0 && !dbg_noweights) slot_fetch();
   };
   // ---- exchanges --------------------------------------------------------------------------------------
   uint32_t ph_ctx = 0, ph_y = 0, ph_hf = 0, ph_part = 0;
@@ -407,11 +468,14 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
                         e1.x + p1.x, e1.y + p1.y, e1.z + p1.z, e1.w + p1.w};
     put_row(v);
   };
-  // attention context of (row `warp`, head c) -> ctx[warp][c*32 ..] of every CTA: lane (jg, dc) serves CTA jg
-  auto send_ctx = [&](const float (&o)[8]) {
-    const uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-    const uint32_t base = cl0 + (lane >> 2) * cl_stride;
-    st_async_v4(base + (smem_u32(&s.ctx[warp][c * HD + (lane & 3) * 8]) - s_local), v,
+  // attention context of (row `warp`, head c) -> ctx[warp][c*32 ..] of every CTA.  A lane holds dims
+  // 4*g4 .. 4*g4+3; with its neighbour (g4 ^ 1) that is one 16-byte piece, sent to CTA (g4 & 1) * 4 + t4.
+  auto send_ctx = [&](const float (&o)[4]) {
+    const uint32_t u0 = pack_bf16(o[0], o[1]), u1 = pack_bf16(o[2], o[3]);
+    const uint32_t w0 = __shfl_xor_sync(0xffffffffu, u0, 4), w1 = __shfl_xor_sync(0xffffffffu, u1, 4);
+    const uint4 v = (g4 & 1) ? make_uint4(w0, w1, u0, u1) : make_uint4(u0, u1, w0, w1);
+    const uint32_t base = cl0 + ((g4 & 1) * 4 + t4) * cl_stride;
+    st_async_v4(base + (smem_u32(&s.ctx[warp][c * HD + (g4 >> 1) * 8]) - s_local), v,
                 base + (smem_u32(&s.xbar[X_CTX]) - s_local));
   };
   // tile of an out-projection -> staging; then 64 threads add bias + residual and send y (4 features each)
@@ -449,6 +513,10 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   if (lane == 0) slot_fetch();
   issue_fpar(0);
 
+  const size_t kv_rh = (size_t)p.cache_blocks * 1024;              // halves per (layer, row, head) region
+  const size_t kv_layer = (size_t)p.rows * NH * kv_rh, kv_row = ((size_t)my_row * NH + c) * kv_rh;
+  const int my_img = my_row / p.beam;
+  const size_t m_layer = (size_t)p.images * NH * 1024, m_row = ((size_t)my_img * NH + c) * 1024;
   int g = 0;     // stream index of the next chunk (chunk g + j belongs to warp (g + j) % 8)
   int gl = 0;    // layer counter of this launch (parity of the fpar double buffer)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
@@ -459,11 +527,13 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       issue_fpar(gl + 1);
       mbar_wait(&s.fpbar[gl & 1], (gl >> 1) & 1);
       const float* fp = s.fpar[gl & 1];
-      const size_t crow = (((size_t)l * p.rows + my_row) * NH + c) * (size_t)p.tmax * HD;   // cache of (row, head c)
-      const size_t mrow = (((size_t)l * p.images + my_row / p.beam) * NH + c) * (size_t)MEM_S * HD;
+      __half* Kc = p.kcache + (size_t)l * kv_layer + kv_row;            // caches of (row `warp`, head c)
+      __half* Vc = p.vcache + (size_t)l * kv_layer + kv_row;
+      const __half* Mk = p.memk + (size_t)l * m_layer + m_row;
+      const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
       TR();
       // ---- self-attention: q, k, v of head c = 6 tiles ---------------------------------------------
-      if (lane < 2) prefetch_l2((lane ? p.memv : p.memk) + mrow, MEM_S * HD * 2);   // this layer's memory K/V -> L2
+      if (lane < 2 && !(p.flags & 2)) prefetch_l2(lane ? Mv : Mk, 2048);   // this layer's memory K/V -> L2
       {
         const int j = (warp - g) & 7;
         if (j < 6) {
@@ -475,12 +545,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           const float b0 = fp[DPC_BQKV + part * HD + f], b1 = fp[DPC_BQKV + part * HD + f + 8];
           const int r0 = 2 * t4;
           if (part == 0) {
-            s.qs[r0][f] = (acc[0] + b0) * ATT_SCALE; s.qs[r0 + 1][f] = (acc[1] + b0) * ATT_SCALE;
-            s.qs[r0][f + 8] = (acc[2] + b1) * ATT_SCALE; s.qs[r0 + 1][f + 8] = (acc[3] + b1) * ATT_SCALE;
+            s.qh[r0][f] = to_half_sat((acc[0] + b0) * ATT_SCALE); s.qh[r0 + 1][f] = to_half_sat((acc[1] + b0) * ATT_SCALE);
+            s.qh[r0][f + 8] = to_half_sat((acc[2] + b1) * ATT_SCALE); s.qh[r0 + 1][f + 8] = to_half_sat((acc[3] + b1) * ATT_SCALE);
           } else {
-            __nv_bfloat16(*dst)[HD] = (part == 1) ? s.knew : s.vnew;
-            dst[r0][f] = __float2bfloat16(acc[0] + b0); dst[r0 + 1][f] = __float2bfloat16(acc[1] + b0);
-            dst[r0][f + 8] = __float2bfloat16(acc[2] + b1); dst[r0 + 1][f + 8] = __float2bfloat16(acc[3] + b1);
+            __half(*dst)[HD] = (part == 1) ? s.knew : s.vnew;
+            dst[r0][f] = to_half_sat(acc[0] + b0); dst[r0 + 1][f] = to_half_sat(acc[1] + b0);
+            dst[r0][f + 8] = to_half_sat(acc[2] + b1); dst[r0 + 1][f + 8] = to_half_sat(acc[3] + b1);
           }
         }
         g += 6;
@@ -488,21 +558,24 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       __syncthreads();
       TR();
       {
-        float o[8];
-        attend<NB>(&s.qs[warp][0], p.kcache + crow, p.vcache + crow, t, &s.knew[warp][0], &s.vnew[warp][0], lane, o);
+        float o[4];
+        long long* tr = (tracing && t == p.trace_step && ti + 3 < 1024) ? p.trace + ti : nullptr;
+        attend_mma<NB, true>(&s.qh[warp][0], Kc, Vc, (p.flags & 8) ? min(t, 1) : t, &s.knew[warp][0], &s.vnew[warp][0],
+                             &s.pbuf[warp][0], lane, o, tr);
+        if (tr) ti += 3;
         send_ctx(o);
-        if (row_ok && lane < 8) {                              // append this step's key / value to the cache
-          const __nv_bfloat16* src = (lane < 4) ? &s.knew[warp][lane * 8] : &s.vnew[warp][(lane - 4) * 8];
-          __nv_bfloat16* dst = ((lane < 4) ? p.kcache : p.vcache) + crow + (size_t)t * HD + (lane & 3) * 8;
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        if (row_ok) {                                          // append this step's key / value (fragment-major)
+          const int blk = t >> 5, kb = t & 31;
+          if (lane < 16)
+            reinterpret_cast<uint32_t*>(Kc + (size_t)blk * 1024)[kfrag_word(kb, lane)] =
+                reinterpret_cast<const uint32_t*>(&s.knew[warp][0])[lane];
+          Vc[(size_t)blk * 1024 + vfrag_half(kb, lane)] = s.vnew[warp][lane];
         }
         // self-attention cache of the NEXT layer (next step's layer 0 after the last one) -> L2
         const int ln = (l + 1 < L) ? l + 1 : 0;
         const int keys = (l + 1 < L) ? t : t + 1;
-        if (lane < 2 && keys > 0 && keys < p.tmax) {
-          const size_t nrow = (((size_t)ln * p.rows + my_row) * NH + c) * (size_t)p.tmax * HD;
-          prefetch_l2((lane ? p.vcache : p.kcache) + nrow, keys * HD * 2);
-        }
+        if (keys > 0 && lane < 2 && !(p.flags & 1))
+          prefetch_l2((lane ? p.vcache : p.kcache) + (size_t)ln * kv_layer + kv_row, ((keys + 31) >> 5) * 2048);
       }
       TR();
       // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
@@ -538,16 +611,16 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           slot_release();
           const int f = j * 16 + g4, r0 = 2 * t4;
           const float b0 = fp[DPC_BCQ + f], b1 = fp[DPC_BCQ + f + 8];
-          s.qs[r0][f] = (acc[0] + b0) * ATT_SCALE; s.qs[r0 + 1][f] = (acc[1] + b0) * ATT_SCALE;
-          s.qs[r0][f + 8] = (acc[2] + b1) * ATT_SCALE; s.qs[r0 + 1][f + 8] = (acc[3] + b1) * ATT_SCALE;
+          s.qh[r0][f] = to_half_sat((acc[0] + b0) * ATT_SCALE); s.qh[r0 + 1][f] = to_half_sat((acc[1] + b0) * ATT_SCALE);
+          s.qh[r0][f + 8] = to_half_sat((acc[2] + b1) * ATT_SCALE); s.qh[r0 + 1][f + 8] = to_half_sat((acc[3] + b1) * ATT_SCALE);
         }
         g += 2;
       }
       __syncthreads();
       TR();
       {
-        float o[8];
-        attend<1>(&s.qs[warp][0], p.memk + mrow, p.memv + mrow, MEM_S, nullptr, nullptr, lane, o);
+        float o[4];
+        attend_mma<1, false>(&s.qh[warp][0], Mk, Mv, MEM_S, nullptr, nullptr, &s.pbuf[warp][0], lane, o, nullptr);
         send_ctx(o);
       }
       TR();
@@ -695,19 +768,31 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
 }
 
 __global__ void repack_memkv_kernel(const __nv_bfloat16* __restrict__ memkv, int images, int L,
-                                    __nv_bfloat16* __restrict__ memk, __nv_bfloat16* __restrict__ memv) {
-  // memkv [img*30+s][l*512 + kv*256 + h*32 + d]  ->  mem{k,v} [l][img][h][s][d]   (16-byte chunks)
-  const size_t total = (size_t)images * MEM_S * L * 2 * NH * 4;
+                                    __half* __restrict__ memk, __half* __restrict__ memv) {
+  // memkv bf16 [img*30+s][l*512 + kv*256 + h*32 + d]  ->  one fragment-major block (32 key slots, keys 30 and 31
+  // zero) of memk and of memv per (l, img, h).  One thread per (l, img, h, kv, key slot).
+  const size_t total = (size_t)L * images * NH * 2 * 32;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = i & 3, h = (i >> 2) & 7, kv = (i >> 5) & 1;
-    const size_t rest = i >> 6;
-    const int l = rest % L;
-    const size_t row = rest / L;              // img*30 + s
-    const int sidx = row % MEM_S;
-    const size_t img = row / MEM_S;
-    const uint4 v = *reinterpret_cast<const uint4*>(memkv + row * (size_t)L * 512 + l * 512 + kv * 256 + h * 32 + ch * 8);
-    __nv_bfloat16* dst = (kv ? memv : memk) + ((((size_t)l * images + img) * NH + h) * MEM_S + sidx) * HD + ch * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
+    const int key = i & 31, kv = (i >> 5) & 1, h = (i >> 6) & 7;
+    const size_t rest = i >> 9;
+    const size_t img = rest % images;
+    const int l = (int)(rest / images);
+    const size_t blk = (((size_t)l * images + img) * NH + h) * 1024;
+    const __nv_bfloat16* src = memkv + (img * MEM_S + min(key, MEM_S - 1)) * (size_t)L * 512 + l * 512 + kv * 256 + h * 32;
+    const bool ok = key < MEM_S;
+    if (kv == 0) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(memk + blk);
+#pragma unroll 4
+      for (int w = 0; w < 16; ++w) {
+        const __half2 v = ok ? __halves2half2(to_half_sat(__bfloat162float(src[2 * w])), to_half_sat(__bfloat162float(src[2 * w + 1])))
+                             : __floats2half2_rn(0.f, 0.f);
+        dst[kfrag_word(key, w)] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+    } else {
+#pragma unroll 4
+      for (int d = 0; d < HD; ++d)
+        memv[blk + vfrag_half(key, d)] = ok ? to_half_sat(__bfloat162float(src[d])) : __float2half(0.f);
+    }
   }
 }
 
@@ -746,6 +831,7 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   HM_CHECK(t_begin >= 0 && t_end > t_begin && t_end <= p.tmax, "decode: bad step range [%d,%d)", t_begin, t_end);
   HM_CHECK(p.fc_tiles % NW == 0 && p.fc_tiles * 16 <= DP_FCB_MAX, "decode: bad fc_tiles %d", p.fc_tiles);
   HM_CHECK(p.chunks_per_step == DP_LAYER_CHUNKS * p.num_layers + p.fc_tiles, "decode: bad chunks_per_step");
+  HM_CHECK(p.cache_blocks * 32 >= p.tmax, "decode: %d cache blocks cannot hold %d positions", p.cache_blocks, p.tmax);
   // 8 rows per cluster; clusters are independent, so a batch larger than 8 x (co-resident clusters)
   // simply runs in several waves.
   dim3 grid(ceil_div(p.rows, R) * CL);
@@ -757,12 +843,11 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   return 0;
 }
 
-int repack_memkv(cudaStream_t st, const __nv_bfloat16* memkv, int images, int L, __nv_bfloat16* memk,
-                 __nv_bfloat16* memv) {
-  const size_t total = (size_t)images * MEM_S * L * 2 * NH * 4;
+int repack_memkv(cudaStream_t st, const __nv_bfloat16* memkv, int images, int L, void* memk, void* memv) {
+  const size_t total = (size_t)L * images * NH * 2 * 32;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  repack_memkv_kernel<<<(int)blocks, 256, 0, st>>>(memkv, images, L, memk, memv);
+  repack_memkv_kernel<<<(int)blocks, 256, 0, st>>>(memkv, images, L, static_cast<__half*>(memk), static_cast<__half*>(memv));
   HM_LAUNCHED();
   return 0;
 }

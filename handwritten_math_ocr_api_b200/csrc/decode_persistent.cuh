@@ -1,5 +1,7 @@
 // Interface of the persistent cluster decode kernel (decode_persistent.cu).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace hmocr {
@@ -40,10 +42,12 @@ struct DecPersistParams {
   const float* fc_bias;       // [8 * 16 * fc_tiles] (zero past the vocabulary)
   const float* emb;           // [vocab][256]
   const float* pos;           // [max_pos][256]
-  __nv_bfloat16* kcache;      // [L][rows][8][tmax][32]
-  __nv_bfloat16* vcache;
-  const __nv_bfloat16* memk;  // [L][images][8][30][32]
-  const __nv_bfloat16* memv;
+  // fp16 caches in mma-fragment-major blocks of 32 keys x 32 dims (2048 bytes, layout in decode_persistent.cu)
+  __half* kcache;             // [L][rows][8][cache_blocks][1024]
+  __half* vcache;             // [L][rows][8][cache_blocks][1024]
+  const __half* memk;         // [L][images][8][1024]   (30 memory tokens, slots 30 and 31 zero)
+  const __half* memv;         // [L][images][8][1024]
+  int cache_blocks;           // ceil(max_seq_len / 32)
   int64_t* tokens;            // [rows][ld_tok]
   float* logprob;             // [rows][max_len] or nullptr
   uint8_t* finished;          // [rows]
@@ -53,12 +57,13 @@ struct DecPersistParams {
   int tmax, max_pos, max_len, ld_tok, eos;
   long long* trace;           // optional: clock64() of cluster 0 / CTA 0 / thread 0 at every phase boundary
   int trace_step;             //           of decode step `trace_step`
+  int flags;                  // developer switches: 1 = no L2 prefetch of the next layer's cache, 2 = none of the memory K/V
 };
 
 int decode_persistent_init();
 int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, int t_end);
 int decode_persistent_max_clusters(int* out);   // co-resident clusters on this device
-int repack_memkv(cudaStream_t st, const __nv_bfloat16* memkv, int images, int L, __nv_bfloat16* memk,
-                 __nv_bfloat16* memv);
+// memkv bf16 [img*30+s][l*512 + kv*256 + h*32 + d] -> the fp16 memk / memv layouts above
+int repack_memkv(cudaStream_t st, const __nv_bfloat16* memkv, int images, int L, void* memk, void* memv);
 
 }  // namespace hmocr

@@ -85,6 +85,7 @@ struct hmocr_engine {
   int decode_impl = 0;                // 0 = persistent cluster kernel, 1 = per-kernel step graph
   int steps_per_launch = 16;
   int trace_step = -1;                // >= 0: record phase-boundary clocks of that decode step
+  int dbg_flags = 0;                  // DecPersistParams::flags
 
   // scratch (grow-only); any reallocation invalidates the captured step graphs
   std::map<std::string, Buf> ws;
@@ -547,17 +548,24 @@ int pack_decode_operands(hmocr_engine* e) {
 int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int64_t* tokens,
                         float* logprob, int32_t* steps, cudaStream_t st) {
   const int nh = e->cfg.nhead, L = e->cfg.num_layers, rows = B;
-  __nv_bfloat16 *memkv, *memk, *memv, *kcache, *vcache;
+  __nv_bfloat16* memkv;
+  __half *memk, *memv, *kcache, *vcache;
   DecodeState* state;
   uint8_t* finished;
-  const int tmax = e->cfg.max_seq_len;
-  const size_t mem_elems = (size_t)B * MEM_S * e->ca_kv.n;
-  HM_TRY(ws_get(e, "gen.memkv", mem_elems, &memkv));
-  HM_TRY(ws_get(e, "gen.memk", mem_elems / 2, &memk));
-  HM_TRY(ws_get(e, "gen.memv", mem_elems / 2, &memv));
-  const size_t cache_elems = (size_t)L * rows * nh * tmax * 32;
-  HM_TRY(ws_get(e, "gen.kcache", cache_elems, &kcache));
-  HM_TRY(ws_get(e, "gen.vcache", cache_elems, &vcache));
+  const int tmax = e->cfg.max_seq_len, cache_blocks = (tmax + 31) / 32;
+  HM_TRY(ws_get(e, "gen.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  HM_TRY(ws_get(e, "dp.memk", (size_t)L * B * nh * 1024, &memk));
+  HM_TRY(ws_get(e, "dp.memv", (size_t)L * B * nh * 1024, &memv));
+  {
+    // whole 32-key blocks are read: the unwritten tail of a block must always hold finite numbers
+    const size_t elems = (size_t)L * rows * nh * cache_blocks * 1024;
+    uint64_t epoch = e->ws_epoch;
+    HM_TRY(ws_get(e, "dp.kcache", elems, &kcache));
+    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(kcache, 0, elems * sizeof(__half), st));
+    epoch = e->ws_epoch;
+    HM_TRY(ws_get(e, "dp.vcache", elems, &vcache));
+    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(vcache, 0, elems * sizeof(__half), st));
+  }
   HM_TRY(ws_get(e, "gen.state", 1, &state));
   HM_TRY(ws_get(e, "gen.finished", rows, &finished));
   HM_TRY(project_memory(e, enc16, B, memkv, st));
@@ -571,8 +579,8 @@ int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int 
   p.rows = rows; p.images = B; p.beam = 1; p.num_layers = L; p.fc_tiles = e->dp_fc_tiles;
   p.chunks_per_step = e->dp_chunks_per_step;
   p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
-  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id;
-  p.trace = nullptr; p.trace_step = e->trace_step;
+  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id; p.cache_blocks = cache_blocks;
+  p.trace = nullptr; p.trace_step = e->trace_step; p.flags = e->dbg_flags;
   if (e->trace_step >= 0) {
     HM_TRY(ws_get(e, "gen.trace", 1024, &p.trace));
     HM_CUDA(cudaMemsetAsync(p.trace, 0, 1024 * sizeof(long long), st));
@@ -803,6 +811,8 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     e->steps_per_launch = value;
   } else if (n == "trace_step") {
     e->trace_step = value;
+  } else if (n == "dbg_flags") {
+    e->dbg_flags = value;
   } else {
     HM_CHECK(false, "unknown option '%s'", name);
   }

@@ -15,7 +15,7 @@ from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib  # noqa:
 from handwritten_math_ocr_api_b200.layout import ModelConfig  # noqa: E402
 from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict  # noqa: E402
 
-LAYER = ["qkv tiles + sync", "self-attention + context send", "wait context 1", "out-proj 1 tiles + y send", "wait y 1",
+LAYER = ["qkv tiles + sync", "self-attn: K loads + scores", "self-attn: softmax", "self-attn: V loads + PV", "self-attn: tail + context send", "wait context 1", "out-proj 1 tiles + y send", "wait y 1",
          "layernorm 1 + sync", "cross-q tiles + sync", "cross-attention + context send", "wait context 2",
          "out-proj 2 tiles + y send", "wait y 2", "layernorm 2 + sync", "linear1 tiles + hidden send", "wait hidden",
          "linear2 tiles + y send", "wait y 3", "layernorm 3 + sync", "next layer: bias wait"]
@@ -24,6 +24,7 @@ TAIL = ["fc_out tiles + warp reduce + sync", "partials send + wait", "token sele
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--step", type=int, default=100)
+ap.add_argument("--flags", type=int, default=0)
 a = ap.parse_args()
 cfg = ModelConfig()
 m = FormulaRecognitionModel(cfg.vocab_size)
@@ -33,6 +34,7 @@ imgs = imgs.repeat((a.batch + 7) // 8, 1, 1, 1)[: a.batch].contiguous()
 enc = m.encoder(imgs)
 m.generate(encoder_out=enc, max_len=150)
 m.set_option("trace_step", a.step)
+m.set_option("dbg_flags", a.flags)
 m.generate(encoder_out=enc, max_len=150)
 torch.cuda.synchronize()
 buf = (C.c_int64 * 1024)()
