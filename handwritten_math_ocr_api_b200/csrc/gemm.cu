@@ -6,13 +6,16 @@
 // /root/reference/src/model_swin.py:45,64,87; torch MultiheadAttention in/out projections,
 // TransformerDecoderLayer.linear1/linear2).
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles
 //              into a STAGES-deep shared-memory ring, completion on "full" mbarriers
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
 //              tcgen05.commit releases the ring slot ("empty") and publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per
-//              thread), fuse bias / GELU / ReLU / fp32 residual / LayerNorm, store fp32 and/or bf16
+//   warps 2-9  epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per
+//              thread), fuse bias / GELU / ReLU / fp32 residual / LayerNorm, store fp32 and/or bf16.
+//              A warp may only touch TMEM lanes [32*(warp%4), +32), so two warps share each lane
+//              quarter and take alternate 32-column chunks: the small-K GEMMs of Swin stage 1/2 are
+//              epilogue-bound, and one epilogue warp per scheduler cannot hide its own latencies.
 // Two TMEM accumulators (2 x BN columns) let the epilogue of tile i overlap the main loop of
 // tile i+1; the producer runs ahead across tile boundaries, so HBM stays busy for the small-K
 // shapes of Swin stage 1/2 where the epilogue dominates.
@@ -27,7 +30,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct Cfg {
@@ -69,9 +73,9 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 
 template <int BN>
 __device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t taddr, int row, bool row_ok,
-                                               int n0) {
+                                               int n0, int c_first) {
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_first; c < BN / 32; c += 2) {
     uint32_t r[32];
     tmem_ld32(taddr + c * 32, r);
     const int col = n0 + c * 32;
@@ -218,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -287,10 +291,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BN;
-      if (p.epi.ln_gamma != nullptr)
-        epilogue_ln<BN>(p.epi, taddr, row, row_ok, n0);
-      else
-        epilogue_plain<BN>(p.epi, taddr, row, row_ok, n0);
+      const int half = (warp - 2) >> 2;    // which of the two warps of this lane quarter
+      if (p.epi.ln_gamma != nullptr) {
+        if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row_ok, n0);     // row statistics: one thread per row
+      } else {
+        epilogue_plain<BN>(p.epi, taddr, row, row_ok, n0, half);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);

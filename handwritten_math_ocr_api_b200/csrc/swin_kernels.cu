@@ -82,6 +82,95 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Src src, int rows, int C
   }
 }
 
+// Specialised LayerNorm for the Swin channel counts: a row is shared by G = C / (4 V) lanes (V float4 per
+// lane), so a warp normalises 32 / G rows at once and every lane moves data (the generic kernel above
+// keeps 8 of 32 lanes idle at C = 96 and spends most of its instructions on predicated-off iterations).
+// Warps walk the rows grid-stride; gamma / beta stay in registers when they fit.
+template <int C, int V, bool MERGE>
+__global__ void __launch_bounds__(256) layernorm_c_kernel(const float* __restrict__ x, int rows, int H, int W,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
+  constexpr int G = C / (4 * V), RPW = 32 / G;
+  static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0 && G * 4 * V == C, "bad LayerNorm geometry");
+  constexpr bool PARAMS_IN_REGS = V <= 3;
+  const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float4 gr[PARAMS_IN_REGS ? V : 1], br[PARAMS_IN_REGS ? V : 1];
+  if (PARAMS_IN_REGS) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      gr[i] = __ldg(reinterpret_cast<const float4*>(gamma) + g + G * i);
+      br[i] = __ldg(reinterpret_cast<const float4*>(beta) + g + G * i);
+    }
+  }
+  for (int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += warps_total * RPW) {
+    const int row = row0 + sub;
+    const bool ok = row < rows;
+    float4 v[V];
+    float sum = 0.f;
+    size_t base00 = 0;
+    if (MERGE) {   // output row (b,i,j) = concat of x[b,2i+dr,2j+dc,:] for (dr,dc) in (0,0),(1,0),(0,1),(1,1)
+      const int Ho = H >> 1, Wo = W >> 1, rr = ok ? row : 0;
+      const int j = rr % Wo, i = (rr / Wo) % Ho, b = rr / (Wo * Ho);
+      base00 = ((size_t)(b * H + 2 * i) * W + 2 * j) * (C / 4);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int idx = g + G * i;                       // float4 index within the row
+      const float4* p;
+      if (MERGE) {
+        constexpr int per = C / 16;                    // float4 per source segment
+        const int sgm = idx / per;
+        p = reinterpret_cast<const float4*>(x + base00 + (size_t)((sgm & 1) * W + (sgm >> 1)) * (C / 4)) + (idx - sgm * per);
+      } else {
+        p = reinterpret_cast<const float4*>(x + (size_t)row * C) + idx;
+      }
+      v[i] = ok ? __ldcs(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + LN_EPS);
+    if (!ok) continue;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int idx = g + G * i;
+      float4 gg, bb;
+      if (PARAMS_IN_REGS) { gg = gr[i]; bb = br[i]; }
+      else {
+        gg = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        bb = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+      }
+      float4 y;
+      y.x = v[i].x * rstd * gg.x + bb.x; y.y = v[i].y * rstd * gg.y + bb.y;
+      y.z = v[i].z * rstd * gg.z + bb.z; y.w = v[i].w * rstd * gg.w + bb.w;
+      if (out16 != nullptr)
+        reinterpret_cast<uint2*>(out16 + (size_t)row * C)[idx] = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      if (out32 != nullptr) reinterpret_cast<float4*>(out32 + (size_t)row * C)[idx] = y;
+    }
+  }
+}
+
+template <int C, int V, bool MERGE>
+int launch_ln_c(cudaStream_t st, const float* x, int rows, int H, int W, const float* gamma, const float* beta,
+                __nv_bfloat16* out16, float* out32) {
+  constexpr int RPW = 32 / (C / (4 * V));
+  int blocks = ceil_div(rows, 8 * RPW);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  layernorm_c_kernel<C, V, MERGE><<<blocks, 256, 0, st>>>(x, rows, H, W, gamma, beta, out16, out32);
+  HM_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Patch embedding: Conv2d(1,96,k4,s4) + NHWC + LayerNorm(96)     swin_transformer.py:556-562
 // one warp per token; lane owns channels lane, lane+32, lane+64
@@ -260,6 +349,13 @@ int layernorm(cudaStream_t st, const float* x, int rows, int C, const float* gam
               __nv_bfloat16* out16, float* out32) {
   HM_CHECK(C % 4 == 0 && C <= LN_MAXV * 128, "layernorm: C=%d unsupported (multiple of 4, <= %d)", C, LN_MAXV * 128);
   HM_CHECK(rows > 0, "layernorm: empty input");
+  switch (C) {      // the Swin-T widths get the lane-exact kernel
+    case 96: return launch_ln_c<96, 3, false>(st, x, rows, 0, 0, gamma, beta, out16, out32);
+    case 192: return launch_ln_c<192, 3, false>(st, x, rows, 0, 0, gamma, beta, out16, out32);
+    case 384: return launch_ln_c<384, 3, false>(st, x, rows, 0, 0, gamma, beta, out16, out32);
+    case 768: return launch_ln_c<768, 6, false>(st, x, rows, 0, 0, gamma, beta, out16, out32);
+    default: break;
+  }
   RowSrc src{x, C};
   layernorm_kernel<RowSrc><<<ceil_div(rows, 8), 256, 0, st>>>(src, rows, C, gamma, beta, out16, out32);
   HM_LAUNCHED();
@@ -271,6 +367,12 @@ int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin
   HM_CHECK(H % 2 == 0 && W % 2 == 0, "patch_merge: odd grid %dx%d (the reference pads; never hit at 96x320)", H, W);
   HM_CHECK(Cin % 4 == 0 && 4 * Cin <= LN_MAXV * 128, "patch_merge: C=%d unsupported", Cin);
   const int rows = B * (H / 2) * (W / 2);
+  switch (Cin) {
+    case 96: return launch_ln_c<384, 3, true>(st, x, rows, H, W, gamma, beta, out16, nullptr);
+    case 192: return launch_ln_c<768, 6, true>(st, x, rows, H, W, gamma, beta, out16, nullptr);
+    case 384: return launch_ln_c<1536, 12, true>(st, x, rows, H, W, gamma, beta, out16, nullptr);
+    default: break;
+  }
   MergeSrc src{x, H, W, Cin};
   layernorm_kernel<MergeSrc><<<ceil_div(rows, 8), 256, 0, st>>>(src, rows, 4 * Cin, gamma, beta, out16, nullptr);
   HM_LAUNCHED();
