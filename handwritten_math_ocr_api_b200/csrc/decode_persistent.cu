@@ -217,28 +217,39 @@ __device__ __forceinline__ int vfrag_half(int key_in_blk, int d) {      // half 
 //   scores:  S[16 keys x 8] = K[16 keys x 32 dims] . q      (q replicated in all 8 columns; two k-steps)
 //   output:  O[16 dims x 8] = Vt[16 dims x 16 keys] . p     (p replicated in all columns; two m-tiles)
 // q is pre-scaled by log2(e)/sqrt(32): the softmax runs on ex2.  Probabilities go through a 64-byte per
-// block shared buffer in P-operand order.  Keys come in blocks of 32; two blocks of K and of V are in flight.
+// block shared buffer in P-operand order.
+// Keys come in blocks of 32 (2 KB of K and 2 KB of V).  Four register slots of one block each form the
+// load pipeline: attend_issue() puts the first four K blocks in flight (it is called BEFORE the block
+// barrier that publishes q, so the barrier wait hides part of the latency); attend_mma() consumes K block
+// b from slot b % 4 and immediately re-arms the slot with K block b+4 or, once the slot has seen its
+// last K block, with V block b % 4 - so the V loads fly while the remaining scores and the softmax are
+// computed.
 // Result: out[j] = context of dim 4*g4 + j (identical in the 4 lanes that share g4).
 // If NEW, one more key/value (this step's own, still in shared memory) is folded in on CUDA cores, so the
 // attention never waits for its own cache append to travel through L2.
+struct KvSlots { uint4 r[4][4]; };
+
+__device__ __forceinline__ void load_block(const uint4* base, int b, uint4 (&d)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = __ldcg(base + 128 * b + 32 * u);
+}
+template <int NB>
+__device__ __forceinline__ void attend_issue(const __half* Kc, int n, int lane, KvSlots& kv) {
+  const int nb = (n + 31) >> 5;
+  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;       // + 128 * block + 32 * fragment
+#pragma unroll
+  for (int b = 0; b < 4 && b < NB; ++b)
+    if (b < nb) load_block(Kl, b, kv.r[b]);
+}
 template <int NB, bool NEW>
 __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, const __half* Vc, int n,
                                            const __half* knew, const __half* vnew, uint32_t* pbuf, int lane,
-                                           float (&out)[4], long long* tr) {
+                                           KvSlots& kv, float (&out)[4], long long* tr) {
   const int g4 = lane >> 2, t4 = lane & 3;
   const uint2 q0 = *reinterpret_cast<const uint2*>(qh + 4 * t4), q1 = *reinterpret_cast<const uint2*>(qh + 16 + 4 * t4);
   const int nb = (n + 31) >> 5;
-  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;       // + 128 * block + 32 * fragment
+  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;
   const uint4* Vl = reinterpret_cast<const uint4*>(Vc) + lane;
-  uint4 kr[2][4], vr[2][4];
-  auto load4 = [&](const uint4* base, int b, uint4 (&d)[4]) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) d[u] = __ldcg(base + 128 * b + 32 * u);
-  };
-  if (0 < nb) load4(Kl, 0, kr[0]);
-  if (NB > 1 && 1 < nb) load4(Kl, 1, kr[1]);
-  if (0 < nb) load4(Vl, 0, vr[0]);
-  if (NB > 1 && 1 < nb) load4(Vl, 1, vr[1]);
   float snew = -INFINITY;
   if (NEW) {
     const uint4 kn = *reinterpret_cast<const uint4*>(knew + t4 * 8), qn = *reinterpret_cast<const uint4*>(qh + t4 * 8);
@@ -258,7 +269,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     if (b < nb) {                                                   // warp-uniform
-      const uint4(&d)[4] = kr[b & 1];
+      uint4(&d)[4] = kv.r[b & 3];
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -268,7 +279,8 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
         sc[4 * b + 2 * tile] = (key < n) ? c[0] : -INFINITY;
         sc[4 * b + 2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
       }
-      if (b + 2 < NB && b + 2 < nb) load4(Kl, b + 2, kr[b & 1]);
+      if (b + 4 < NB && b + 4 < nb) load_block(Kl, b + 4, d);       // next K block of this slot ...
+      else load_block(Vl, b & 3, d);                                // ... or its first V block (b & 3 < nb here)
     } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) sc[4 * b + u] = -INFINITY;
@@ -290,7 +302,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
         const __half2 ph = __floats2half2_rn(ex2f(sc[4 * b + 2 * tile] - m), ex2f(sc[4 * b + 2 * tile + 1] - m));
         const float2 pf = __half22float2(ph);                       // normalise with the rounded weights
         den += pf.x + pf.y;
-        if (t4 == 0) pw[16 * b + 8 * tile] = *reinterpret_cast<const uint32_t*>(&ph);
+        pw[16 * b + 8 * tile] = *reinterpret_cast<const uint32_t*>(&ph);   // same word from the 4 lanes of a group
       }
     }
   }
@@ -300,14 +312,14 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     if (b < nb) {
-      const uint4(&d)[4] = vr[b & 1];
+      uint4(&d)[4] = kv.r[b & 3];
       const uint2 p0 = *reinterpret_cast<const uint2*>(pbuf + 16 * b + 2 * t4);
       const uint2 p1 = *reinterpret_cast<const uint2*>(pbuf + 16 * b + 8 + 2 * t4);
       mma_f16(acc0, d[0].x, d[0].y, d[0].z, d[0].w, p0.x, p0.y);
       mma_f16(acc1, d[1].x, d[1].y, d[1].z, d[1].w, p0.x, p0.y);
       mma_f16(acc0, d[2].x, d[2].y, d[2].z, d[2].w, p1.x, p1.y);
       mma_f16(acc1, d[3].x, d[3].y, d[3].z, d[3].w, p1.x, p1.y);
-      if (b + 2 < NB && b + 2 < nb) load4(Vl, b + 2, vr[b & 1]);
+      if (b + 4 < NB && b + 4 < nb) load_block(Vl, b + 4, d);
     }
   }
 #pragma unroll
@@ -555,13 +567,16 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         }
         g += 6;
       }
+      KvSlots kv;
+      const int nhist = (p.flags & 8) ? min(t, 1) : t;
+      attend_issue<NB>(Kc, nhist, lane, kv);       // history K blocks fly across the barrier
       __syncthreads();
       TR();
       {
         float o[4];
         long long* tr = (tracing && t == p.trace_step && ti + 3 < 1024) ? p.trace + ti : nullptr;
-        attend_mma<NB, true>(&s.qh[warp][0], Kc, Vc, (p.flags & 8) ? min(t, 1) : t, &s.knew[warp][0], &s.vnew[warp][0],
-                             &s.pbuf[warp][0], lane, o, tr);
+        attend_mma<NB, true>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0], lane,
+                             kv, o, tr);
         if (tr) ti += 3;
         send_ctx(o);
         if (row_ok) {                                          // append this step's key / value (fragment-major)
@@ -616,11 +631,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         }
         g += 2;
       }
+      attend_issue<1>(Mk, MEM_S, lane, kv);
       __syncthreads();
       TR();
       {
         float o[4];
-        attend_mma<1, false>(&s.qh[warp][0], Mk, Mv, MEM_S, nullptr, nullptr, &s.pbuf[warp][0], lane, o, nullptr);
+        attend_mma<1, false>(&s.qh[warp][0], Mk, Mv, MEM_S, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
         send_ctx(o);
       }
       TR();
