@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 T_MAX = 150
+CPU_SAMPLE_IMAGES = 8                # bounded CPU sample: one batch of 8 images x 150 full-prefix greedy steps (~3 s on 16 cores)
 ENC_GFLOP_PER_IMAGE = 6.515          # reference-executed; 5.498 if padded rows are skipped
 ENC_GFLOP_MINIMAL = 5.498
 
@@ -61,6 +62,19 @@ def decode_algorithmic_bytes(batch: int, T: int, layers=8, d=256, S=30, weight_p
     return batch * per_seq + weight_params * 2 * T
 
 
+def decode_traffic_from_ncu(batch: int, T: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel launches of ONE step, from the
+    committed ncu capture (profiles/decode_traffic.json); None if no capture matches this workload."""
+    f = os.path.join(ROOT, "profiles", "decode_traffic.json")
+    try:
+        d = json.load(open(f))
+        if d.get("batch") == batch and d.get("max_len") == T:
+            return d["dram_bytes_per_step"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -72,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -127,7 +141,7 @@ def cpu_reference_sample(n_images: int, max_len: int, reps: int, warmup: int):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_img, max_len = 2, T_MAX
+    n_img, max_len = CPU_SAMPLE_IMAGES, T_MAX
     r = cpu_reference_sample(n_img, max_len, reps=args.steps, warmup=min(args.warmup, 1))
     mean = sum(r["times"]) / len(r["times"])
     ips = n_img / mean
@@ -264,8 +278,11 @@ def run_ours(args, rank, local_rank, world):
                        "weights": "synthetic seed 0 (oracle/synth.py, eos never emitted)",
                        "parallelism": f"dp{world}"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                         "kernel": "decode phase (150 replays of the captured step graph), bf16 KV",
+                         "frac": ach / pk["hbm_gbs"], "traffic": decode_traffic_from_ncu(B, T),
+                         "peak_source": pk["source"],
+                         "kernel": "decode_persistent_kernel: the decode phase of one step = ceil(150/16) launches of "
+                                   "the persistent cluster kernel (+ memory K/V projection); bytes and CUDA-event time "
+                                   "are summed over them; 2-byte (fp16) KV caches",
                          "algorithmic_bytes_per_step": dec_bytes,
                          "encoder": {"bound": "tensor", "achieved": enc_tf, "peak": pk["bf16_tflops_sustained"],
                                      "unit": "TFLOP/s", "frac": enc_tf / pk["bf16_tflops_sustained"],
@@ -277,11 +294,12 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            r = cpu_reference_sample(2, T, reps=1, warmup=0)
+            r = cpu_reference_sample(CPU_SAMPLE_IMAGES, T, reps=3, warmup=0)
             m = sum(r["times"]) / len(r["times"])
-            line["cpu_baseline"] = {"value": 2 / m, "unit": "images/s", "cores": r["cores"], "kind": "port",
-                                    "sample": "2 images x 150 greedy steps, oracle port of src/inference.py "
-                                              "(full-prefix recompute, torch eager fp32), 1 repetition"}
+            line["cpu_baseline"] = {"value": CPU_SAMPLE_IMAGES / m, "unit": "images/s", "cores": r["cores"],
+                                    "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_IMAGES} images x 150 greedy steps in one batch, oracle port of "
+                                              "src/inference.py (full-prefix recompute, torch eager fp32), mean of 3 repetitions"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -291,7 +309,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)

@@ -11,7 +11,7 @@
 // So each SM streams only 1/8 of the decoder weights per step.
 //
 // Math.  Projections run as  C^T[16 features x 8 rows] = W[16 x K] . X^T  with mma.sync.m16n8k16
-// (bf16 in, fp32 accumulate): the WEIGHTS are the M=16 operand and the cluster's 8 rows are exactly
+// (fp16 in, fp32 accumulate): the WEIGHTS are the M=16 operand and the cluster's 8 rows are exactly
 // the N=8 operand, so no tensor-core lane is wasted and one weight fragment is read from shared
 // memory exactly once.  tcgen05 needs M >= 64 rows and the step does 13-15 MFLOP per token: this
 // kernel is latency/bandwidth bound, not tensor bound.
@@ -57,10 +57,10 @@ struct __align__(16) Partial { float m; int idx; float s; int pad; };
 struct Smem {
   alignas(128) uint8_t slot[NW][DP_CHUNK];  // warp-private weight slots
   alignas(16) float y32[R][D];              // pre-LayerNorm rows gathered from the 8 feature slices
-  alignas(16) __nv_bfloat16 xa[R][PD];      // LayerNorm output (full rows), bf16 operand
-  alignas(16) __nv_bfloat16 ctx[R][PD];     // attention context gathered from the 8 heads
-  alignas(16) __nv_bfloat16 hf[R][PF];      // relu(linear1) gathered from the 8 slices
-  alignas(16) float stg[4][16][9];          // staging of GEMM tiles [task][feature][row] (hidden: bf16 [8][72])
+  alignas(16) __half xa[R][PD];             // LayerNorm output (full rows), fp16 operand
+  alignas(16) __half ctx[R][PD];            // attention context gathered from the 8 heads
+  alignas(16) __half hf[R][PF];             // relu(linear1) gathered from the 8 slices
+  alignas(16) float stg[4][16][9];          // staging of GEMM tiles [task][feature][row] (hidden: fp16 [8][72])
   alignas(16) float x32s[R][32];            // fp32 residual stream, this CTA's 32-feature slice only
   alignas(16) __half qh[R][HD];             // this head's scaled query (fp16 mma operand)
   alignas(16) uint32_t pbuf[NW][128];       // per-warp softmax probabilities in P-operand order (half2 words)
@@ -77,7 +77,7 @@ struct Smem {
 enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3 };
 constexpr uint32_t XB_CTX = R * D * 2, XB_Y = R * D * 4, XB_HF = R * FF * 2, XB_PART = CL * R * sizeof(Partial);
 static_assert(sizeof(Smem) <= 112 * 1024, "two CTAs must fit one SM");
-static_assert(sizeof(float) * 4 * 16 * 9 >= sizeof(__nv_bfloat16) * R * 72, "hidden staging aliases stg");
+static_assert(sizeof(float) * 4 * 16 * 9 >= sizeof(__half) * R * 72, "hidden staging aliases stg");
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -142,19 +142,25 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
       "{%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+__device__ __forceinline__ uint32_t pack_half(float a, float b) {
+  const __half2 v = __halves2half2(to_half_sat(a), to_half_sat(b));
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 // C^T[16 features x 8 rows] = W[16 x 256] (one weight chunk, pitch PD) . X[8 rows x 256]^T (smem, pitch PB)
 //   c[0]: (feature lane/4, row 2*(lane%4)), c[1]: (same feature, row + 1), c[2], c[3]: feature + 8
 // Four independent accumulator chains keep the tensor pipe busy from a single warp.
 template <int PB>
-__device__ __forceinline__ void gemm16(const uint8_t* W, const __nv_bfloat16* X, int lane, float (&c)[4]) {
+__device__ __forceinline__ void gemm16(const uint8_t* W, const __half* X, int lane, float (&c)[4]) {
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -166,22 +172,12 @@ __device__ __forceinline__ void gemm16(const uint8_t* W, const __nv_bfloat16* X,
     ldsm_x4(b_addr + kk * 64, b);
     ldsm_x4(a_addr + kk * 64, a0);
     ldsm_x4(a_addr + kk * 64 + 32, a1);
-    mma_bf16(acc[(2 * kk) & 3], a0, b[0], b[1]);
-    mma_bf16(acc[(2 * kk + 1) & 3], a1, b[2], b[3]);
+    mma_f16(acc[(2 * kk) & 3], a0[0], a0[1], a0[2], a0[3], b[0], b[1]);
+    mma_f16(acc[(2 * kk + 1) & 3], a1[0], a1[1], a1[2], a1[3], b[2], b[3]);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) c[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
 }
-
-__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                        uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -449,7 +445,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       *reinterpret_cast<float4*>(&s.x32s[warp][(lane & 3) * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
     }
     *reinterpret_cast<uint4*>(&s.xa[warp][lane * 8]) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        make_uint4(pack_half(v[0], v[1]), pack_half(v[2], v[3]), pack_half(v[4], v[5]), pack_half(v[6], v[7]));
   };
   // LayerNorm of the gathered rows: warp w owns row w; lane owns 8 consecutive columns
   auto layer_norm = [&](const LnRegs& ln) {
@@ -483,7 +479,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   // attention context of (row `warp`, head c) -> ctx[warp][c*32 ..] of every CTA.  A lane holds dims
   // 4*g4 .. 4*g4+3; with its neighbour (g4 ^ 1) that is one 16-byte piece, sent to CTA (g4 & 1) * 4 + t4.
   auto send_ctx = [&](const float (&o)[4]) {
-    const uint32_t u0 = pack_bf16(o[0], o[1]), u1 = pack_bf16(o[2], o[3]);
+    const uint32_t u0 = pack_half(o[0], o[1]), u1 = pack_half(o[2], o[3]);
     const uint32_t w0 = __shfl_xor_sync(0xffffffffu, u0, 4), w1 = __shfl_xor_sync(0xffffffffu, u1, 4);
     const uint4 v = (g4 & 1) ? make_uint4(w0, w1, u0, u1) : make_uint4(u0, u1, w0, w1);
     const uint32_t base = cl0 + ((g4 & 1) * 4 + t4) * cl_stride;
@@ -670,11 +666,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
           slot_release();
-          __nv_bfloat16(*hs)[72] = reinterpret_cast<__nv_bfloat16(*)[72]>(&s.stg[0][0][0]);
+          __half(*hs)[72] = reinterpret_cast<__half(*)[72]>(&s.stg[0][0][0]);
           const int f = j * 16 + g4, r0 = 2 * t4;
           const float b0 = fp[DPC_B1 + f], b1 = fp[DPC_B1 + f + 8];
-          hs[r0][f] = __float2bfloat16(fmaxf(acc[0] + b0, 0.f)); hs[r0 + 1][f] = __float2bfloat16(fmaxf(acc[1] + b0, 0.f));
-          hs[r0][f + 8] = __float2bfloat16(fmaxf(acc[2] + b1, 0.f)); hs[r0 + 1][f + 8] = __float2bfloat16(fmaxf(acc[3] + b1, 0.f));
+          hs[r0][f] = to_half_sat(fmaxf(acc[0] + b0, 0.f)); hs[r0 + 1][f] = to_half_sat(fmaxf(acc[1] + b0, 0.f));
+          hs[r0][f + 8] = to_half_sat(fmaxf(acc[2] + b1, 0.f)); hs[r0 + 1][f + 8] = to_half_sat(fmaxf(acc[3] + b1, 0.f));
           named_bar_sync(2, 128);
           if (j < 2) {
             const int u = j * 32 + lane, r = u >> 3, piece = u & 7;
@@ -783,9 +779,9 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   cluster_sync_all();      // no CTA exits while a peer may still address its shared memory
 }
 
-__global__ void repack_memkv_kernel(const __nv_bfloat16* __restrict__ memkv, int images, int L,
+__global__ void repack_memkv_kernel(const float* __restrict__ memkv, int images, int L,
                                     __half* __restrict__ memk, __half* __restrict__ memv) {
-  // memkv bf16 [img*30+s][l*512 + kv*256 + h*32 + d]  ->  one fragment-major block (32 key slots, keys 30 and 31
+  // memkv f32 [img*30+s][l*512 + kv*256 + h*32 + d]  ->  one fragment-major block (32 key slots, keys 30 and 31
   // zero) of memk and of memv per (l, img, h).  One thread per (l, img, h, kv, key slot).
   const size_t total = (size_t)L * images * NH * 2 * 32;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -794,20 +790,20 @@ __global__ void repack_memkv_kernel(const __nv_bfloat16* __restrict__ memkv, int
     const size_t img = rest % images;
     const int l = (int)(rest / images);
     const size_t blk = (((size_t)l * images + img) * NH + h) * 1024;
-    const __nv_bfloat16* src = memkv + (img * MEM_S + min(key, MEM_S - 1)) * (size_t)L * 512 + l * 512 + kv * 256 + h * 32;
+    const float* src = memkv + (img * MEM_S + min(key, MEM_S - 1)) * (size_t)L * 512 + l * 512 + kv * 256 + h * 32;
     const bool ok = key < MEM_S;
     if (kv == 0) {
       uint32_t* dst = reinterpret_cast<uint32_t*>(memk + blk);
 #pragma unroll 4
       for (int w = 0; w < 16; ++w) {
-        const __half2 v = ok ? __halves2half2(to_half_sat(__bfloat162float(src[2 * w])), to_half_sat(__bfloat162float(src[2 * w + 1])))
+        const __half2 v = ok ? __halves2half2(to_half_sat(src[2 * w]), to_half_sat(src[2 * w + 1]))
                              : __floats2half2_rn(0.f, 0.f);
         dst[kfrag_word(key, w)] = *reinterpret_cast<const uint32_t*>(&v);
       }
     } else {
 #pragma unroll 4
       for (int d = 0; d < HD; ++d)
-        memv[blk + vfrag_half(key, d)] = ok ? to_half_sat(__bfloat162float(src[d])) : __float2half(0.f);
+        memv[blk + vfrag_half(key, d)] = ok ? to_half_sat(src[d]) : __float2half(0.f);
     }
   }
 }
@@ -859,7 +855,7 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   return 0;
 }
 
-int repack_memkv(cudaStream_t st, const __nv_bfloat16* memkv, int images, int L, void* memk, void* memv) {
+int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, void* memk, void* memv) {
   const size_t total = (size_t)L * images * NH * 2 * 32;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -6,7 +6,7 @@
 
 namespace hmocr {
 
-// Packed weight stream (bf16).  One chunk = one mma m-tile of a projection: 16 weight rows (output
+// Packed weight stream (fp16: same bytes as bf16, 3 more mantissa bits; values are saturated to +-65504).  One chunk = one mma m-tile of a projection: 16 weight rows (output
 // features) x 256 input columns, rows padded to 264 elements so ldmatrix is bank-conflict free.
 // Every chunk is one cp.async.bulk copy of DP_CHUNK bytes.
 //
@@ -63,7 +63,7 @@ struct DecPersistParams {
 int decode_persistent_init();
 int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, int t_end);
 int decode_persistent_max_clusters(int* out);   // co-resident clusters on this device
-// memkv bf16 [img*30+s][l*512 + kv*256 + h*32 + d] -> the fp16 memk / memv layouts above
-int repack_memkv(cudaStream_t st, const __nv_bfloat16* memkv, int images, int L, void* memk, void* memv);
+// memkv f32 [img*30+s][l*512 + kv*256 + h*32 + d] -> the fp16 memk / memv layouts above
+int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, void* memk, void* memv);
 
 }  // namespace hmocr

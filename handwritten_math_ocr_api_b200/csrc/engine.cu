@@ -455,12 +455,14 @@ int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B
 // operand packing for decode_persistent.cu (host side, once at load)
 // ------------------------------------------------------------------------------------------------
 // 16 weight rows [row0, row0+16) x 256 input columns [col0, col0+256) of a [valid_rows, K] fp32 matrix -> one
-// stream chunk (bf16 [16][264], zero padded)
-void pack_chunk(std::vector<__nv_bfloat16>& dst, size_t off, const float* w, int row0, int col0, int K, int valid_rows) {
+// stream chunk (fp16 [16][264], zero padded)
+void pack_chunk(std::vector<__half>& dst, size_t off, const float* w, int row0, int col0, int K, int valid_rows) {
   for (int r = 0; r < DP_CH_ROWS; ++r)
     for (int k = 0; k < 264; ++k) {
       const bool ok = (k < 256) && (row0 + r < valid_rows);
-      dst[off + (size_t)r * 264 + k] = __float2bfloat16(ok ? w[(size_t)(row0 + r) * K + col0 + k] : 0.f);
+      float v = ok ? w[(size_t)(row0 + r) * K + col0 + k] : 0.f;
+      v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+      dst[off + (size_t)r * 264 + k] = __float2half(v);
     }
 }
 
@@ -474,7 +476,7 @@ int pack_decode_operands(hmocr_engine* e) {
   e->dp_fc_tiles = ((V + 127) / 128 + 7) / 8 * 8;      // 16-row tiles per CTA, a multiple of the 8 warps
   e->dp_chunks_per_step = DP_LAYER_CHUNKS * L + e->dp_fc_tiles;
   const size_t S = (size_t)e->dp_chunks_per_step, CE = DP_CHUNK / 2;        // chunk size in elements
-  std::vector<__nv_bfloat16> stream(8 * S * CE);
+  std::vector<__half> stream(8 * S * CE);
   std::vector<float> fpar((size_t)L * 8 * DP_FPC), lnpar((size_t)L * 6 * d);
   for (int l = 0; l < L; ++l) {
     const std::string p = "decoder.decoder.layers." + std::to_string(l) + ".";
@@ -548,12 +550,12 @@ int pack_decode_operands(hmocr_engine* e) {
 int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int64_t* tokens,
                         float* logprob, int32_t* steps, cudaStream_t st) {
   const int nh = e->cfg.nhead, L = e->cfg.num_layers, rows = B;
-  __nv_bfloat16* memkv;
+  float* memkv;                       // memory K/V of all layers, fp32 out of the GEMM, fp16 after the repack
   __half *memk, *memv, *kcache, *vcache;
   DecodeState* state;
   uint8_t* finished;
   const int tmax = e->cfg.max_seq_len, cache_blocks = (tmax + 31) / 32;
-  HM_TRY(ws_get(e, "gen.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  HM_TRY(ws_get(e, "dp.memkv32", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
   HM_TRY(ws_get(e, "dp.memk", (size_t)L * B * nh * 1024, &memk));
   HM_TRY(ws_get(e, "dp.memv", (size_t)L * B * nh * 1024, &memv));
   {
@@ -568,7 +570,11 @@ int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int 
   }
   HM_TRY(ws_get(e, "gen.state", 1, &state));
   HM_TRY(ws_get(e, "gen.finished", rows, &finished));
-  HM_TRY(project_memory(e, enc16, B, memkv, st));
+  {
+    GemmEpilogue ek;
+    ek.out_f32 = memkv; ek.ld32 = e->ca_kv.n;
+    HM_TRY(run_lin(st, enc16, e->cfg.d_model, B * MEM_S, e->ca_kv, ek));
+  }
   HM_TRY(repack_memkv(st, memkv, B, L, memk, memv));
   HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   DecPersistParams p;

@@ -16,6 +16,10 @@ pytestmark = pytest.mark.gpu
 
 FEAT_TOL = 6e-2
 LOGIT_TOL = 1.5e-1
+# the persistent decode kernel on identical encoder features (fp16 operands, fp32 accumulate / residual /
+# LayerNorm / softmax): measured max |log p(winner) - oracle| 1.3e-2, largest oracle margin at a divergence 1.8e-2
+DECODE_LOGP_TOL = 5e-2
+DECODE_TIE_MARGIN = 6e-2
 
 
 @pytest.fixture(scope="module")
@@ -209,3 +213,91 @@ def test_errors_are_loud(model):
         fresh.encoder(torch.zeros(1, 1, 96, 320))
     with pytest.raises(RuntimeError):
         fresh.load_state_dict({"encoder.features.0.0.weight": torch.zeros(96, 1, 4, 4)})
+
+
+def _check_tokens_against_logits(got, ys, logits, what):
+    """Tokens identical, or the first divergence sits at a near-tie of the oracle's logits."""
+    top2 = logits.topk(2, -1).values
+    margin = (top2[..., 0] - top2[..., 1]).numpy()
+    same = 0
+    for r, c in _first_divergence(got, ys.numpy()):
+        if c is None:
+            same += 1
+            continue
+        m = float(margin[r, c - 1])
+        assert m < DECODE_TIE_MARGIN, f"{what}: row {r} diverges at column {c} where the oracle margin is {m:.3f}"
+    return same
+
+
+def test_long_sequences_max_seq_len_256(golden_src):
+    """BASELINE.json config 5 (T = 256): legal only when config.max_seq_len is raised before the model is built
+    (SURVEY.md D6).  Exercises the 8-block (256-key) variant of the decode kernel."""
+    from handwritten_math_ocr_api_b200 import FormulaRecognitionModel
+    from handwritten_math_ocr_api_b200.config import Config
+    from oracle import decode as odec
+    from oracle.arch import ModelConfig
+    from oracle.synth import synth_images, synth_state_dict
+
+    class Config256(Config):
+        max_seq_len = 256
+
+    cfg = ModelConfig(max_seq_len=256)
+    sd = synth_state_dict(cfg, seed=0, eos_bias_sigma=0.0)
+    m = FormulaRecognitionModel(cfg.vocab_size, config=Config256())
+    m.load_state_dict(sd)
+    imgs = synth_images(3, int(golden_src["images_seed"]))
+    enc = m.encoder(imgs.cuda())
+    tokens, steps, _ = m.generate(encoder_out=enc, max_len=256)
+    assert steps == 256 and tokens.shape == (3, 257)
+    ys, lg = odec.greedy_cached(enc.cpu(), sd, cfg, max_len=256, return_logits=True)
+    _check_tokens_against_logits(tokens.cpu().numpy(), ys, lg, "T=256")
+    with pytest.raises(RuntimeError):
+        m.generate(encoder_out=enc, max_len=257)
+
+
+def test_batch_larger_than_one_wave(model, golden_src):
+    """More rows than 8 x (co-resident clusters): the clusters of one launch run in several waves."""
+    from oracle.synth import synth_images
+    imgs = synth_images(4, int(golden_src["images_seed"])).cuda()
+    base, _, _ = model.generate(imgs, max_len=20)
+    B = 300
+    big = imgs.repeat(B // 4, 1, 1, 1).contiguous()
+    tok, steps, _ = model.generate(big, max_len=20)
+    n = min(tok.shape[1], base.shape[1])
+    for r in range(B):
+        assert torch.equal(tok[r, :n], base[r % 4, :n])
+
+
+def test_greedy_agreement_on_a_larger_sample(model, sd, cfg):
+    """north_star: greedy sequences identical on >= 99.9 % of inputs, any divergence traced to a near-tie.
+    64 fresh images, 60 free-running steps, against the fp32 oracle run on the SAME encoder features.  With the
+    synthetic (random) checkpoint the logits are nearly flat - the oracle's own top-1/top-2 margin is below
+    3e-2 on ~17 % of steps - so what is asserted is the part that does not depend on the
+    weights: EVERY divergence starts at a near-tie, and the winner's log-probability matches the oracle's
+    until then."""
+    from oracle import decode as odec
+    from oracle.synth import synth_images
+    imgs = synth_images(64, seed=4321)
+    enc = model.encoder(imgs.cuda())
+    tokens, steps, logp = model.generate(encoder_out=enc, max_len=60, return_logprobs=True)
+    ys, lg = odec.greedy_cached(enc.cpu(), sd, cfg, max_len=60, return_logits=True)
+    got = tokens.cpu().numpy()
+    same = _check_tokens_against_logits(got, ys, lg, "agreement")
+    ref_lp = torch.log_softmax(lg, -1).gather(-1, ys[:, 1:].unsqueeze(-1)).squeeze(-1).numpy()
+    ours = logp.cpu().numpy()
+    top2 = lg.topk(2, -1).values
+    margin = (top2[..., 0] - top2[..., 1]).numpy()
+    err, agree_steps, total, div_margins = 0.0, 0, 0, []
+    for r, c in _first_divergence(got, ys.numpy()):
+        n = (c - 1) if c is not None else min(ours.shape[1], ref_lp.shape[1])
+        if c is not None:
+            div_margins.append(float(margin[r, c - 1]))
+        if n > 0:
+            err = max(err, float(np.abs(ours[r, :n] - ref_lp[r, :n]).max()))
+        agree_steps += n
+        total += min(ours.shape[1], ref_lp.shape[1])
+    print(f"identical greedy sequences: {same}/64; steps before the first divergence: {agree_steps}/{total}; "
+          f"max |log p(winner) - oracle| on agreeing prefixes: {err:.4f}; oracle margins at the divergences: "
+          f"max {max(div_margins) if div_margins else 0:.4f}, median {float(np.median(div_margins)) if div_margins else 0:.4f}")
+    assert err < DECODE_LOGP_TOL
+    assert same >= 40
