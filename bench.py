@@ -166,7 +166,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib
-    from handwritten_math_ocr_api_b200.parallel import gather_tokens
+    from handwritten_math_ocr_api_b200.parallel import gather_tokens, gather_tokens_device
     from handwritten_math_ocr_api_b200.layout import ModelConfig
     from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict
 
@@ -185,10 +185,13 @@ def run_ours(args, rank, local_rank, world):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def step_device():
-        tokens, steps, _ = model.generate(dev_imgs, max_len=T)
-        if world > 1:
-            gather_tokens(tokens, pad_id=model.pad_id)          # the path's only collective (NCCL)
-        return tokens, steps
+        if world == 1:
+            tokens, steps, _ = model.generate(dev_imgs, max_len=T)
+            return tokens, steps
+        # stream-ordered: decode -> the path's only collective (NCCL all-gather of the ids) -> one host read
+        tok, st, _ = model.generate_device(dev_imgs, max_len=T)
+        all_tok, all_steps = gather_tokens_device(tok, st)
+        return all_tok, int(all_steps.max().item())
 
     def barrier():
         if world > 1:
@@ -229,12 +232,21 @@ def run_ours(args, rank, local_rank, world):
     tok_host = torch.empty(B, T + 1, dtype=torch.int64).pin_memory()
     steps_host = torch.zeros(1, dtype=torch.int32).pin_memory()
 
+    all_host = torch.empty(world * B, T + 1, dtype=torch.int64).pin_memory() if world > 1 else None
+
     def step_e2e():
-        _lib.check(lib.hmocr_generate_host(model._handle(), C.c_void_p(host_imgs.data_ptr()), B, T, 1,
-                                           C.c_void_p(tok_host.data_ptr()), None, C.c_void_p(steps_host.data_ptr()),
-                                           None, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "generate_host")
-        if world > 1:
-            gather_tokens(tok_host.to(dev, non_blocking=True), pad_id=model.pad_id)
+        if world == 1:
+            _lib.check(lib.hmocr_generate_host(model._handle(), C.c_void_p(host_imgs.data_ptr()), B, T, 1,
+                                               C.c_void_p(tok_host.data_ptr()), None, C.c_void_p(steps_host.data_ptr()),
+                                               None, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "generate_host")
+            return
+        # host images in, gathered ids of the whole job out (every rank reads them), all stream-ordered
+        x = host_imgs.to(dev, non_blocking=True)
+        tok, st, _ = model.generate_device(x, max_len=T)
+        all_tok, all_steps = gather_tokens_device(tok, st)
+        all_host.copy_(all_tok, non_blocking=True)
+        steps_host.copy_(all_steps.max().to(torch.int32).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
     step_e2e()
     barrier()
     e0 = time.perf_counter()
@@ -289,7 +301,7 @@ def run_ours(args, rank, local_rank, world):
                                      "gflop_per_image": ENC_GFLOP_PER_IMAGE,
                                      "gflop_per_image_minimal": ENC_GFLOP_MINIMAL}},
             "e2e": {"value": total_imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * 96 * 320 * 4,
-                    "d2h_bytes_per_step": B * (T + 1) * 8 + 4},
+                    "d2h_bytes_per_step": (B if world == 1 else world * B) * (T + 1) * 8 + 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -225,6 +225,27 @@ class FormulaRecognitionModel:
 
     # ---- the fast path ---------------------------------------------------------------------------
     @torch.no_grad()
+    def generate_device(self, images: Optional[torch.Tensor] = None, max_len: Optional[int] = None,
+                        return_logprobs: bool = False, encoder_out: Optional[torch.Tensor] = None):
+        """``generate`` without the host synchronisation: everything stays on the stream.
+
+        Returns ``(tokens int64 [B, 1+max_len], steps int32 [1] (device), logprobs f32 [B, max_len] | None)``;
+        columns past ``steps`` hold ``pad``.  Used where the result feeds another stream-ordered operation
+        (the multi-GPU token gather) so the GPU never idles waiting for the host."""
+        max_len = int(max_len if max_len is not None else self.max_seq_len)
+        lib = self._eng.lib
+        x = self._images(images) if encoder_out is None else encoder_out.to(device=self.device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        tokens = torch.empty(B, max_len + 1, dtype=torch.int64, device=self.device)
+        logp = torch.empty(B, max_len, dtype=torch.float32, device=self.device) if return_logprobs else None
+        steps = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            fn = lib.hmocr_generate if encoder_out is None else lib.hmocr_generate_from_memory
+            _lib.check(fn(self._handle(), _ptr(x), B, max_len, 1, _ptr(tokens), _ptr(logp), _ptr(steps), None, _stream()),
+                       "hmocr_generate")
+        return tokens, steps, logp
+
+    @torch.no_grad()
     def generate(self, images: Optional[torch.Tensor] = None, max_len: Optional[int] = None, beam_size: int = 1,
                  return_logprobs: bool = False, encoder_out: Optional[torch.Tensor] = None):
         """Greedy (beam_size=1) or beam decode in ONE library call.

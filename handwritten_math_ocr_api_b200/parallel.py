@@ -45,6 +45,22 @@ def gather_tokens(tokens: torch.Tensor, pad_id: int = 0, group=None) -> torch.Te
     return torch.cat(rows, 0)
 
 
+def gather_tokens_device(tokens_full: torch.Tensor, steps: torch.Tensor, group=None):
+    """Stream-ordered gather for equal per-rank batches: ``tokens_full`` is the full-width
+    ``[B, 1+max_len]`` buffer of ``generate_device`` (pad past each rank's own step count), ``steps`` its
+    int32 ``[1]`` device counter.  Two collectives, no host synchronisation, no metadata exchange:
+    returns ``(tokens [world*B, 1+max_len], steps [world])`` still on the device."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return tokens_full, steps
+    world = dist.get_world_size(group)
+    out = torch.empty(world * tokens_full.shape[0], tokens_full.shape[1], dtype=tokens_full.dtype,
+                      device=tokens_full.device)
+    all_steps = torch.empty(world, dtype=steps.dtype, device=steps.device)
+    dist.all_gather_into_tensor(out, tokens_full.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_steps, steps, group=group)
+    return out, all_steps
+
+
 def generate_sharded(model, images: torch.Tensor, max_len: Optional[int] = None, group=None) -> torch.Tensor:
     """Every rank passes the same full batch (or any object with ``shape[0]``); each decodes its
     contiguous shard with ``model.generate`` and all ranks return the full ``[N, 1+steps]`` ids."""

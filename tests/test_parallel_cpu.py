@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from handwritten_math_ocr_api_b200.parallel import gather_tokens, generate_sharded, shard_bounds
+from handwritten_math_ocr_api_b200.parallel import gather_tokens, gather_tokens_device, generate_sharded, shard_bounds
 
 
 def test_shard_bounds_cover_everything():
@@ -52,6 +52,11 @@ def _worker(rank, world, port, n_images, q):
         # ragged direct gather: rank r holds r+1 rows of r+2 columns
         mine = torch.full((rank + 1, rank + 2), rank + 10, dtype=torch.int64)
         rag = gather_tokens(mine, pad_id=0)
+        # stream-ordered variant: equal batches, full-width buffers, per-rank step counters
+        tok = torch.full((2, 5), rank + 20, dtype=torch.int64)
+        dev_tok, dev_steps = gather_tokens_device(tok, torch.tensor([rank + 3], dtype=torch.int32))
+        assert dev_tok.shape == (2 * world, 5) and dev_tok[2 * rank].tolist() == [rank + 20] * 5
+        assert dev_steps.tolist() == [3 + r for r in range(world)]
         q.put((rank, full.tolist(), rag.tolist()))       # plain lists: no shared-memory handles in the queue
     finally:
         dist.destroy_process_group()
