@@ -68,10 +68,7 @@ struct Smem {
   alignas(16) __half vnew[R][HD];
   Partial part[CL][R];                      // per-CTA argmax / sum-exp partials (gathered)
   Partial wpart[NW][R];                     // per-warp partials
-  alignas(16) float fpar[2][DP_FPC];        // this CTA's bias slices of layer l / l+1
-  alignas(16) float fcb[DP_FCB_MAX];        // this CTA's slice of fc_out.bias
   alignas(8) uint64_t full[NW];
-  alignas(8) uint64_t fpbar[2];
   alignas(8) uint64_t xbar[4];              // exchange barriers: context, y, hidden, partials
 };
 enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3 };
@@ -360,6 +357,12 @@ __device__ __forceinline__ Partial shfl_partial(const Partial& a, int o) {
 
 struct LnRegs { float4 g0, g1, b0, b1; };
 
+// The fp32 bias of weight row r travels in the padding of that row (halves 256, 257 of 264): it arrives with
+// the weights, costs no extra copy, barrier or shared memory, and is read before the slot is released.
+__device__ __forceinline__ float chunk_bias(const uint8_t* slot, int r) {
+  return *reinterpret_cast<const float*>(slot + (r * PD + D) * 2);
+}
+
 template <int NB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
@@ -419,15 +422,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       st_async_v4(base + off, v, base + boff);
     }
   };
-  // per-layer bias slices of this CTA, double buffered: layer counter gl = step * L + l
-  const int total_layers = (t_end - t_begin) * L;
-  auto issue_fpar = [&](int gl) {
-    if (tid == 0 && gl < total_layers) {
-      const int l = gl % L;
-      mbar_expect_tx(&s.fpbar[gl & 1], DP_FPC * 4);
-      bulk_g2s(s.fpar[gl & 1], p.fparams + ((size_t)l * CL + c) * DP_FPC, DP_FPC * 4, &s.fpbar[gl & 1]);
-    }
-  };
   // LayerNorm gamma/beta of this lane's 8 columns, fetched (L2) a phase ahead of their use
   auto load_ln = [&](int l, int which) {
     const float* g = p.lnparams + ((size_t)l * 6 + 2 * which) * D + lane * 8;
@@ -452,14 +446,21 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     const float4 a = *reinterpret_cast<const float4*>(&s.y32[warp][lane * 8]);
     const float4 b = *reinterpret_cast<const float4*>(&s.y32[warp][lane * 8 + 4]);
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    float sum = 0.f;
+    // one pass: sum and sum of squares reduced together (5 shuffle rounds instead of 10).  The rows are
+    // residual + projection of normalised activations (|mean| well below the spread), so E[x^2] - mean^2 in
+    // fp32 loses nothing that matters; clamped at 0 for safety.
+    float sum = 0.f, sq = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sum += v[e];
-    const float mean = warp_sum(sum) * (1.0f / D);
-    float sq = 0.f;
+    for (int e = 0; e < 8; ++e) { sum += v[e]; sq = fmaf(v[e], v[e], sq); }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { v[e] -= mean; sq += v[e] * v[e]; }
-    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + LN_EPS);
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean = sum * (1.0f / D);
+    const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + LN_EPS);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] -= mean;
     v[0] = v[0] * rstd * ln.g0.x + ln.b0.x; v[1] = v[1] * rstd * ln.g0.y + ln.b0.y;
     v[2] = v[2] * rstd * ln.g0.z + ln.b0.z; v[3] = v[3] * rstd * ln.g0.w + ln.b0.w;
     v[4] = v[4] * rstd * ln.g1.x + ln.b1.x; v[5] = v[5] * rstd * ln.g1.y + ln.b1.y;
@@ -487,17 +488,17 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
                 base + (smem_u32(&s.xbar[X_CTX]) - s_local));
   };
   // tile of an out-projection -> staging; then 64 threads add bias + residual and send y (4 features each)
-  auto stage_tile = [&](int slot_idx, const float (&acc)[4]) {
-    s.stg[slot_idx][g4][2 * t4] = acc[0]; s.stg[slot_idx][g4][2 * t4 + 1] = acc[1];
-    s.stg[slot_idx][g4 + 8][2 * t4] = acc[2]; s.stg[slot_idx][g4 + 8][2 * t4 + 1] = acc[3];
+  auto stage_tile = [&](int slot_idx, const float (&acc)[4], float b0, float b1) {     // + the chunk's bias
+    s.stg[slot_idx][g4][2 * t4] = acc[0] + b0; s.stg[slot_idx][g4][2 * t4 + 1] = acc[1] + b0;
+    s.stg[slot_idx][g4 + 8][2 * t4] = acc[2] + b1; s.stg[slot_idx][g4 + 8][2 * t4 + 1] = acc[3] + b1;
   };
-  auto send_y = [&](int u, const float* bias, bool two_partials) {   // u in [0, 64): row u/8, features 4*(u%8) ..
+  auto send_y = [&](int u, bool two_partials) {   // u in [0, 64): row u/8, features 4*(u%8) ..
     const int r = u >> 3, fq = u & 7, mt = fq >> 2, f0 = (fq & 3) * 4;
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = two_partials ? s.stg[2 * mt][f0 + e][r] + s.stg[2 * mt + 1][f0 + e][r] : s.stg[mt][f0 + e][r];
-      v[e] = a + bias[fq * 4 + e] + s.x32s[r][fq * 4 + e];
+      v[e] = a + s.x32s[r][fq * 4 + e];
     }
     send_all(&s.y32[r][c * 32 + fq * 4],
              make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), X_Y);
@@ -505,8 +506,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
 
   if (tid == 0) {
     for (int i = 0; i < NW; ++i) mbar_init(&s.full[i], 1);
-    mbar_init(&s.fpbar[0], 1);
-    mbar_init(&s.fpbar[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&s.xbar[i], 1);
     fence_barrier_init();
     mbar_expect_tx(&s.xbar[X_CTX], XB_CTX);
@@ -514,27 +513,24 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     mbar_expect_tx(&s.xbar[X_HF], XB_HF);
     mbar_expect_tx(&s.xbar[X_PART], XB_PART);
   }
-  for (int i = tid; i < cols_per_cta; i += THREADS) s.fcb[i] = p.fc_bias[c * cols_per_cta + i];
   embed_row(t_begin, p.tokens[(size_t)my_row * p.ld_tok + t_begin]);
   __syncthreads();
   cluster_sync_all();      // every CTA of the cluster is resident and its barriers are armed before any DSMEM store
   if (lane == 0) slot_fetch();
-  issue_fpar(0);
 
   const size_t kv_rh = (size_t)p.cache_blocks * 1024;              // halves per (layer, row, head) region
   const size_t kv_layer = (size_t)p.rows * NH * kv_rh, kv_row = ((size_t)my_row * NH + c) * kv_rh;
   const int my_img = my_row / p.beam;
   const size_t m_layer = (size_t)p.images * NH * 1024, m_row = ((size_t)my_img * NH + c) * 1024;
   int g = 0;     // stream index of the next chunk (chunk g + j belongs to warp (g + j) % 8)
-  int gl = 0;    // layer counter of this launch (parity of the fpar double buffer)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
   int ti = 0;
 #define TR() do { if (tracing && t == p.trace_step && ti < 1024) p.trace[ti++] = clock64(); } while (0)
   for (int t = t_begin; t < t_end; ++t) {
-    for (int l = 0; l < L; ++l, ++gl) {
-      issue_fpar(gl + 1);
-      mbar_wait(&s.fpbar[gl & 1], (gl >> 1) & 1);
-      const float* fp = s.fpar[gl & 1];
+    // where this step's key / value go inside the (layer, row, head) region of the fragment-major caches
+    const int k_app = (t >> 5) * 512 + kfrag_word(t & 31, lane & 15);       // 32-bit word index (lanes 0..15)
+    const int v_app = (t >> 5) * 1024 + vfrag_half(t & 31, lane);           // half index (lane = dim)
+    for (int l = 0; l < L; ++l) {
       __half* Kc = p.kcache + (size_t)l * kv_layer + kv_row;            // caches of (row `warp`, head c)
       __half* Vc = p.vcache + (size_t)l * kv_layer + kv_row;
       const __half* Mk = p.memk + (size_t)l * m_layer + m_row;
@@ -546,11 +542,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         const int j = (warp - g) & 7;
         if (j < 6) {
           float acc[4];
+          const int part = j >> 1, f = (j & 1) * 16 + g4;               // 0 = q, 1 = k, 2 = v; feature f, f+8 of the head
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
+          const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
           slot_release();
-          const int part = j >> 1, f = (j & 1) * 16 + g4;               // 0 = q, 1 = k, 2 = v; feature f, f+8 of the head
-          const float b0 = fp[DPC_BQKV + part * HD + f], b1 = fp[DPC_BQKV + part * HD + f + 8];
           const int r0 = 2 * t4;
           if (part == 0) {
             s.qh[r0][f] = to_half_sat((acc[0] + b0) * ATT_SCALE); s.qh[r0 + 1][f] = to_half_sat((acc[1] + b0) * ATT_SCALE);
@@ -576,11 +572,8 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         if (tr) ti += 3;
         send_ctx(o);
         if (row_ok) {                                          // append this step's key / value (fragment-major)
-          const int blk = t >> 5, kb = t & 31;
-          if (lane < 16)
-            reinterpret_cast<uint32_t*>(Kc + (size_t)blk * 1024)[kfrag_word(kb, lane)] =
-                reinterpret_cast<const uint32_t*>(&s.knew[warp][0])[lane];
-          Vc[(size_t)blk * 1024 + vfrag_half(kb, lane)] = s.vnew[warp][lane];
+          if (lane < 16) reinterpret_cast<uint32_t*>(Kc)[k_app] = reinterpret_cast<const uint32_t*>(&s.knew[warp][0])[lane];
+          Vc[v_app] = s.vnew[warp][lane];
         }
         // self-attention cache of the NEXT layer (next step's layer 0 after the last one) -> L2
         const int ln = (l + 1 < L) ? l + 1 : 0;
@@ -599,10 +592,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           float acc[4];
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.ctx[0][0], lane, acc);
+          const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
           slot_release();
-          stage_tile(j, acc);
+          stage_tile(j, acc, b0, b1);
           named_bar_sync(1, 64);
-          send_y(j * 32 + lane, fp + DPC_BO, false);
+          send_y(j * 32 + lane, false);
         }
         g += 2;
       }
@@ -617,11 +611,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         const int j = (warp - g) & 7;
         if (j < 2) {
           float acc[4];
+          const int f = j * 16 + g4, r0 = 2 * t4;
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
+          const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
           slot_release();
-          const int f = j * 16 + g4, r0 = 2 * t4;
-          const float b0 = fp[DPC_BCQ + f], b1 = fp[DPC_BCQ + f + 8];
           s.qh[r0][f] = to_half_sat((acc[0] + b0) * ATT_SCALE); s.qh[r0 + 1][f] = to_half_sat((acc[1] + b0) * ATT_SCALE);
           s.qh[r0][f + 8] = to_half_sat((acc[2] + b1) * ATT_SCALE); s.qh[r0 + 1][f + 8] = to_half_sat((acc[3] + b1) * ATT_SCALE);
         }
@@ -645,10 +639,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           float acc[4];
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.ctx[0][0], lane, acc);
+          const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
           slot_release();
-          stage_tile(j, acc);
+          stage_tile(j, acc, b0, b1);
           named_bar_sync(1, 64);
-          send_y(j * 32 + lane, fp + DPC_BCO, false);
+          send_y(j * 32 + lane, false);
         }
         g += 2;
       }
@@ -663,12 +658,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         const int j = (warp - g) & 7;
         if (j < 4) {
           float acc[4];
+          const int f = j * 16 + g4, r0 = 2 * t4;
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
+          const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
           slot_release();
           __half(*hs)[72] = reinterpret_cast<__half(*)[72]>(&s.stg[0][0][0]);
-          const int f = j * 16 + g4, r0 = 2 * t4;
-          const float b0 = fp[DPC_B1 + f], b1 = fp[DPC_B1 + f + 8];
           hs[r0][f] = to_half_sat(fmaxf(acc[0] + b0, 0.f)); hs[r0 + 1][f] = to_half_sat(fmaxf(acc[1] + b0, 0.f));
           hs[r0][f + 8] = to_half_sat(fmaxf(acc[2] + b1, 0.f)); hs[r0 + 1][f + 8] = to_half_sat(fmaxf(acc[3] + b1, 0.f));
           named_bar_sync(2, 128);
@@ -689,10 +684,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           float acc[4];
           slot_wait();
           gemm16<PF>(s.slot[warp], &s.hf[0][(j & 1) * 256], lane, acc);
+          const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);   // zero in the kh = 1 chunk
           slot_release();
-          stage_tile(j, acc);
+          stage_tile(j, acc, b0, b1);
           named_bar_sync(3, 128);
-          if (j < 2) send_y(j * 32 + lane, fp + DPC_B2, true);
+          if (j < 2) send_y(j * 32 + lane, true);
         }
         g += 4;
       }
@@ -714,9 +710,9 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         float acc[4];
         slot_wait();
         gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
+        const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
         slot_release();
         const int lf = m * 16 + g4, v0 = c * cols_per_cta + lf;
-        const float b0 = s.fcb[lf], b1 = s.fcb[lf + 8];
         if (v0 < p.vocab) { update_partial(pa, acc[0] + b0, v0); update_partial(pb, acc[1] + b0, v0); }
         if (v0 + 8 < p.vocab) { update_partial(pa, acc[2] + b1, v0 + 8); update_partial(pb, acc[3] + b1, v0 + 8); }
       }
@@ -841,7 +837,7 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   HM_TRY(decode_persistent_init());
   HM_CHECK(p.tmax <= 256, "decode: max_seq_len %d > 256", p.tmax);
   HM_CHECK(t_begin >= 0 && t_end > t_begin && t_end <= p.tmax, "decode: bad step range [%d,%d)", t_begin, t_end);
-  HM_CHECK(p.fc_tiles % NW == 0 && p.fc_tiles * 16 <= DP_FCB_MAX, "decode: bad fc_tiles %d", p.fc_tiles);
+  HM_CHECK(p.fc_tiles % NW == 0 && p.fc_tiles > 0, "decode: bad fc_tiles %d", p.fc_tiles);
   HM_CHECK(p.chunks_per_step == DP_LAYER_CHUNKS * p.num_layers + p.fc_tiles, "decode: bad chunks_per_step");
   HM_CHECK(p.cache_blocks * 32 >= p.tmax, "decode: %d cache blocks cannot hold %d positions", p.cache_blocks, p.tmax);
   // 8 rows per cluster; clusters are independent, so a batch larger than 8 x (co-resident clusters)

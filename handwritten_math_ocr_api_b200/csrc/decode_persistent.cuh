@@ -24,22 +24,13 @@ constexpr int DP_CH_ROWS = 16;
 constexpr int DP_CHUNK = DP_CH_ROWS * 264 * 2;   // 8448 B
 constexpr int DP_LAYER_CHUNKS = 20;
 
-// fp32 bias slices of one (layer, CTA): DP_FPC floats, one bulk copy per layer.
-constexpr int DPC_BQKV = 0;     // in_proj_bias q|k|v of head c            [3][32]
-constexpr int DPC_BO = 96;      // self out_proj.bias[c*32 ..]             [32]
-constexpr int DPC_BCQ = 128;    // cross in_proj_bias q of head c          [32]
-constexpr int DPC_BCO = 160;    // cross out_proj.bias[c*32 ..]            [32]
-constexpr int DPC_B1 = 192;     // linear1.bias[c*64 ..]                   [64]
-constexpr int DPC_B2 = 256;     // linear2.bias[c*32 ..]                   [32]
-constexpr int DP_FPC = 288;
-constexpr int DP_FCB_MAX = 1024;    // max vocabulary columns per CTA (vocab <= 8192)
+// The fp32 bias of every weight row travels in the padding of that row (halves 256, 257 of 264); the second
+// input-half chunks of linear2 carry zeros.
 constexpr int DP_ROWS = 8;          // sequences owned by one cluster (= the N of mma.m16n8k16)
 
 struct DecPersistParams {
   const uint8_t* wstream;     // [8][chunks_per_step][DP_CHUNK]
-  const float* fparams;       // [L][8][DP_FPC] per-(layer, CTA) bias slices
   const float* lnparams;      // [L][6][256]: norm1.weight, norm1.bias, norm2.weight, ... norm3.bias
-  const float* fc_bias;       // [8 * 16 * fc_tiles] (zero past the vocabulary)
   const float* emb;           // [vocab][256]
   const float* pos;           // [max_pos][256]
   // fp16 caches in mma-fragment-major blocks of 32 keys x 32 dims (2048 bytes, layout in decode_persistent.cu)

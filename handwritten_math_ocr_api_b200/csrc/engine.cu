@@ -80,7 +80,7 @@ struct hmocr_engine {
   Lin fc;
   // packed operands of the persistent cluster decode kernel (decode_persistent.cuh)
   uint8_t* dp_wstream = nullptr;
-  float *dp_fparams = nullptr, *dp_fcbias = nullptr, *dp_lnparams = nullptr;
+  float* dp_lnparams = nullptr;
   int dp_fc_tiles = 0, dp_chunks_per_step = 0;
   int decode_impl = 0;                // 0 = persistent cluster kernel, 1 = per-kernel step graph
   int steps_per_launch = 16;
@@ -456,14 +456,19 @@ int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B
 // ------------------------------------------------------------------------------------------------
 // 16 weight rows [row0, row0+16) x 256 input columns [col0, col0+256) of a [valid_rows, K] fp32 matrix -> one
 // stream chunk (fp16 [16][264], zero padded)
-void pack_chunk(std::vector<__half>& dst, size_t off, const float* w, int row0, int col0, int K, int valid_rows) {
-  for (int r = 0; r < DP_CH_ROWS; ++r)
+// `bias` (may be null): fp32 bias of the same rows, stored in the padding of each row (halves 256, 257)
+void pack_chunk(std::vector<__half>& dst, size_t off, const float* w, const float* bias, int row0, int col0, int K,
+                int valid_rows) {
+  for (int r = 0; r < DP_CH_ROWS; ++r) {
     for (int k = 0; k < 264; ++k) {
       const bool ok = (k < 256) && (row0 + r < valid_rows);
       float v = ok ? w[(size_t)(row0 + r) * K + col0 + k] : 0.f;
       v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
       dst[off + (size_t)r * 264 + k] = __float2half(v);
     }
+    const float b = (bias != nullptr && row0 + r < valid_rows) ? bias[row0 + r] : 0.f;
+    memcpy(&dst[off + (size_t)r * 264 + 256], &b, sizeof(float));
+  }
 }
 
 int pack_decode_operands(hmocr_engine* e) {
@@ -472,12 +477,11 @@ int pack_decode_operands(hmocr_engine* e) {
   HM_CHECK(d == 256 && ff == 512 && c.nhead == 8,
            "the persistent decode kernel is specialised for d_model=256, nhead=8, dim_feedforward=512 "
            "(reference config.py:19-21); got %d/%d/%d", d, c.nhead, ff);
-  HM_CHECK(V <= 8 * DP_FCB_MAX, "vocab_size %d exceeds the persistent decode kernel's limit %d", V, 8 * DP_FCB_MAX);
   e->dp_fc_tiles = ((V + 127) / 128 + 7) / 8 * 8;      // 16-row tiles per CTA, a multiple of the 8 warps
   e->dp_chunks_per_step = DP_LAYER_CHUNKS * L + e->dp_fc_tiles;
   const size_t S = (size_t)e->dp_chunks_per_step, CE = DP_CHUNK / 2;        // chunk size in elements
   std::vector<__half> stream(8 * S * CE);
-  std::vector<float> fpar((size_t)L * 8 * DP_FPC), lnpar((size_t)L * 6 * d);
+  std::vector<float> lnpar((size_t)L * 6 * d);
   for (int l = 0; l < L; ++l) {
     const std::string p = "decoder.decoder.layers." + std::to_string(l) + ".";
     const HostTensor *sin, *sinb, *so, *sob, *cin, *cinb, *co, *cob, *w1, *b1, *w2, *b2;
@@ -496,13 +500,13 @@ int pack_decode_operands(hmocr_engine* e) {
     for (int ct = 0; ct < 8; ++ct) {
       size_t off = ((size_t)ct * S + (size_t)l * DP_LAYER_CHUNKS) * CE;
       for (int part = 0; part < 3; ++part)             // q, k, v rows of head ct
-        for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, sin->f.data(), part * d + ct * 32 + 16 * m, 0, d, 3 * d);
-      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, so->f.data(), ct * 32 + 16 * m, 0, d, d);
-      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, cin->f.data(), ct * 32 + 16 * m, 0, d, 3 * d);
-      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, co->f.data(), ct * 32 + 16 * m, 0, d, d);
-      for (int m = 0; m < 4; ++m, off += CE) pack_chunk(stream, off, w1->f.data(), ct * 64 + 16 * m, 0, d, ff);
+        for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, sin->f.data(), sinb->f.data(), part * d + ct * 32 + 16 * m, 0, d, 3 * d);
+      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, so->f.data(), sob->f.data(), ct * 32 + 16 * m, 0, d, d);
+      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, cin->f.data(), cinb->f.data(), ct * 32 + 16 * m, 0, d, 3 * d);
+      for (int m = 0; m < 2; ++m, off += CE) pack_chunk(stream, off, co->f.data(), cob->f.data(), ct * 32 + 16 * m, 0, d, d);
+      for (int m = 0; m < 4; ++m, off += CE) pack_chunk(stream, off, w1->f.data(), b1->f.data(), ct * 64 + 16 * m, 0, d, ff);
       for (int m = 0; m < 2; ++m)
-        for (int kh = 0; kh < 2; ++kh, off += CE) pack_chunk(stream, off, w2->f.data(), ct * 32 + 16 * m, 256 * kh, ff, d);
+        for (int kh = 0; kh < 2; ++kh, off += CE) pack_chunk(stream, off, w2->f.data(), kh == 0 ? b2->f.data() : nullptr, ct * 32 + 16 * m, 256 * kh, ff, d);
     }
     const char* ln[3] = {"norm1", "norm2", "norm3"};
     for (int i = 0; i < 3; ++i) {
@@ -512,36 +516,22 @@ int pack_decode_operands(hmocr_engine* e) {
       memcpy(&lnpar[((size_t)l * 6 + 2 * i) * d], lg->f.data(), sizeof(float) * d);
       memcpy(&lnpar[((size_t)l * 6 + 2 * i + 1) * d], lb->f.data(), sizeof(float) * d);
     }
-    for (int ct = 0; ct < 8; ++ct) {          // the slices CTA `ct` needs (decode_persistent.cuh DPC_*)
-      float* fp = &fpar[((size_t)l * 8 + ct) * DP_FPC];
-      for (int part = 0; part < 3; ++part)
-        memcpy(fp + DPC_BQKV + part * 32, sinb->f.data() + part * d + ct * 32, sizeof(float) * 32);
-      memcpy(fp + DPC_BO, sob->f.data() + ct * 32, sizeof(float) * 32);
-      memcpy(fp + DPC_BCQ, cinb->f.data() + ct * 32, sizeof(float) * 32);
-      memcpy(fp + DPC_BCO, cob->f.data() + ct * 32, sizeof(float) * 32);
-      memcpy(fp + DPC_B1, b1->f.data() + ct * 64, sizeof(float) * 64);
-      memcpy(fp + DPC_B2, b2->f.data() + ct * 32, sizeof(float) * 32);
-    }
   }
   const int cols_per_cta = e->dp_fc_tiles * 16;
-  std::vector<float> fcbias((size_t)8 * cols_per_cta, 0.f);
   {
     const HostTensor *w, *b;
     HM_TRY(need(e, "decoder.fc_out.weight", {V, d}, &w));
     HM_TRY(need(e, "decoder.fc_out.bias", {V}, &b));
     for (int ct = 0; ct < 8; ++ct)
       for (int m = 0; m < e->dp_fc_tiles; ++m)
-        pack_chunk(stream, ((size_t)ct * S + (size_t)L * DP_LAYER_CHUNKS + m) * CE, w->f.data(), ct * cols_per_cta + 16 * m,
-                   0, d, V);
-    memcpy(fcbias.data(), b->f.data(), sizeof(float) * V);
+        pack_chunk(stream, ((size_t)ct * S + (size_t)L * DP_LAYER_CHUNKS + m) * CE, w->f.data(), b->f.data(),
+                   ct * cols_per_cta + 16 * m, 0, d, V);
   }
   void* q;
   HM_TRY(arena_alloc(e, stream.size() * 2, &q));
   HM_CUDA(cudaMemcpy(q, stream.data(), stream.size() * 2, cudaMemcpyHostToDevice));
   e->dp_wstream = static_cast<uint8_t*>(q);
-  HM_TRY(upload_f32(e, fpar.data(), fpar.size(), &e->dp_fparams));
   HM_TRY(upload_f32(e, lnpar.data(), lnpar.size(), &e->dp_lnparams));
-  HM_TRY(upload_f32(e, fcbias.data(), fcbias.size(), &e->dp_fcbias));
   return 0;
 }
 
@@ -578,7 +568,7 @@ int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int 
   HM_TRY(repack_memkv(st, memkv, B, L, memk, memv));
   HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   DecPersistParams p;
-  p.wstream = e->dp_wstream; p.fparams = e->dp_fparams; p.fc_bias = e->dp_fcbias;
+  p.wstream = e->dp_wstream;
   p.lnparams = e->dp_lnparams;
   p.emb = e->emb; p.pos = e->pos; p.kcache = kcache; p.vcache = vcache; p.memk = memk; p.memv = memv;
   p.tokens = tokens; p.logprob = logprob; p.finished = finished; p.state = state;
