@@ -6,11 +6,14 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 namespace hmocr {
+
+typedef __half h16;     // 16-bit activations / weights / caches
 
 // ------------------------------------------------------------------------------------------
 // error handling (host)
@@ -136,8 +139,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, single CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, single CTA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -205,13 +208,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+// The library's 16-bit storage type is IEEE fp16 (same bytes as fp16, 3 more mantissa bits); every
+// fp32 -> fp16 conversion saturates to +-65504 instead of producing inf.
+__device__ __forceinline__ uint32_t pack16(float a, float b) {      // low half = a, high half = b
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack16(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ __half to_h16(float x) {
+  const uint32_t r = pack16(x, 0.f);
+  return __ushort_as_half(static_cast<unsigned short>(r & 0xffffu));
 }
 
 }  // namespace hmocr

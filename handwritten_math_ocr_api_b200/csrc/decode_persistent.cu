@@ -33,7 +33,7 @@
 // key), softmax in fp32, then O = V^T p with 16 head dims as the M operand (fp16 V cache stored
 // TRANSPOSED, [dim][key], so its fragments are also plain 16-byte global loads); probabilities pass
 // through a 512-byte per-warp shared buffer.  ~45 instructions per 32 keys instead of ~200 on CUDA
-// cores; two 32-key blocks of K and of V are in flight per warp.  The caches are fp16 (not bf16): same
+// cores; two 32-key blocks of K and of V are in flight per warp.  The caches are fp16 (not fp16): same
 // bytes, 3 more mantissa bits.  The cache rows of the NEXT layer are pulled into L2
 // (cp.async.bulk.prefetch.L2) one layer ahead.
 //
@@ -147,11 +147,8 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
-__device__ __forceinline__ uint32_t pack_half(float a, float b) {
-  const __half2 v = __halves2half2(to_half_sat(a), to_half_sat(b));
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
+__device__ __forceinline__ __half to_half_sat(float x) { return to_h16(x); }                 // saturating (common.cuh)
+__device__ __forceinline__ uint32_t pack_half(float a, float b) { return pack16(a, b); }
 
 // C^T[16 features x 8 rows] = W[16 x 256] (one weight chunk, pitch PD) . X[8 rows x 256]^T (smem, pitch PB)
 //   c[0]: (feature lane/4, row 2*(lane%4)), c[1]: (same feature, row + 1), c[2], c[3]: feature + 8
@@ -432,7 +429,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     r.b1 = __ldg(reinterpret_cast<const float4*>(g + D + 4));
     return r;
   };
-  // finish a row: bf16 operand row + this CTA's fp32 residual slice
+  // finish a row: fp16 operand row + this CTA's fp32 residual slice
   auto put_row = [&](const float (&v)[8]) {
     if ((lane >> 2) == c) {                              // features c*32 .. c*32+31 live in lanes 4c .. 4c+3
       *reinterpret_cast<float4*>(&s.x32s[warp][(lane & 3) * 8]) = make_float4(v[0], v[1], v[2], v[3]);
@@ -544,6 +541,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           float acc[4];
           const int part = j >> 1, f = (j & 1) * 16 + g4;               // 0 = q, 1 = k, 2 = v; feature f, f+8 of the head
           slot_wait();
+          TR();
           gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
           const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
           slot_release();
@@ -562,6 +560,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       KvSlots kv;
       const int nhist = (p.flags & 8) ? min(t, 1) : t;
       attend_issue<NB>(Kc, nhist, lane, kv);       // history K blocks fly across the barrier
+      TR();
       __syncthreads();
       TR();
       {

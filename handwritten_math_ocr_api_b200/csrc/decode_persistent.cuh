@@ -6,7 +6,7 @@
 
 namespace hmocr {
 
-// Packed weight stream (fp16: same bytes as bf16, 3 more mantissa bits; values are saturated to +-65504).  One chunk = one mma m-tile of a projection: 16 weight rows (output
+// Packed weight stream (fp16: same bytes as fp16, 3 more mantissa bits; values are saturated to +-65504).  One chunk = one mma m-tile of a projection: 16 weight rows (output
 // features) x 256 input columns, rows padded to 264 elements so ldmatrix is bank-conflict free.
 // Every chunk is one cp.async.bulk copy of DP_CHUNK bytes.
 //

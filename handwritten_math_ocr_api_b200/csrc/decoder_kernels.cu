@@ -10,12 +10,12 @@ namespace {
 constexpr int HD = 32;
 constexpr float ATT_SCALE = 0.17677669529663687f;   // 1/sqrt(32)
 
-__device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&out)[HD]) {
+__device__ __forceinline__ void load_row32(const h16* p, float (&out)[HD]) {
   const uint4* p4 = reinterpret_cast<const uint4*>(p);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint4 u = p4[c];
-    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    float2 a = unpack16(u.x), b = unpack16(u.y), cc = unpack16(u.z), d = unpack16(u.w);
     out[8 * c] = a.x; out[8 * c + 1] = a.y; out[8 * c + 2] = b.x; out[8 * c + 3] = b.y;
     out[8 * c + 4] = cc.x; out[8 * c + 5] = cc.y; out[8 * c + 6] = d.x; out[8 * c + 7] = d.y;
   }
@@ -23,7 +23,7 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&out)[
 
 // Warp-cooperative single-query attention over `n` keys (n <= 32*MAXK).
 //   q      : the query (already scaled), replicated in every lane
-//   K(j)/V(j): pointer to the 32 bf16 of key/value j
+//   K(j)/V(j): pointer to the 32 fp16 of key/value j
 // Lane l scores keys l, l+32, ...; softmax by warp shuffles; lane d then accumulates output
 // channel d (coalesced 64-byte V rows).  Returns out[d] in lane d.
 constexpr int MAXK = 8;   // up to 256 keys
@@ -62,7 +62,7 @@ __device__ __forceinline__ float warp_attend(const float (&q)[HD], int n, KF K, 
       const int cnt = min(32, n - base);
       for (int jj = 0; jj < cnt; ++jj) {
         const float p = __shfl_sync(0xffffffffu, sc[i], jj);
-        acc = fmaf(p, __bfloat162float(V(base + jj)[lane]), acc);
+        acc = fmaf(p, __half2float(V(base + jj)[lane]), acc);
       }
     }
   }
@@ -72,7 +72,7 @@ __device__ __forceinline__ float warp_attend(const float (&q)[HD], int n, KF K, 
 __global__ void __launch_bounds__(256) embed_kernel(const int64_t* __restrict__ tok, int ld_tok, int rows, int T,
                                                     const float* __restrict__ emb, const float* __restrict__ pos,
                                                     int d, int vocab, float* __restrict__ x32,
-                                                    __nv_bfloat16* __restrict__ x16) {
+                                                    h16* __restrict__ x16) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(256) embed_kernel(const int64_t* __restrict__ 
     const float4 p = *reinterpret_cast<const float4*>(pos + (size_t)t * d + c);
     const float4 y = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
     *reinterpret_cast<float4*>(x32 + (size_t)r * d + c) = y;
-    *reinterpret_cast<uint2*>(x16 + (size_t)r * d + c) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    *reinterpret_cast<uint2*>(x16 + (size_t)r * d + c) = make_uint2(pack16(y.x, y.y), pack16(y.z, y.w));
   }
 }
 
 // ---- teacher-forced attention ----------------------------------------------------------------
-__global__ void __launch_bounds__(256) prefill_self_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T,
-                                                           int nhead, __nv_bfloat16* __restrict__ ctx) {
+__global__ void __launch_bounds__(256) prefill_self_kernel(const h16* __restrict__ qkv, int B, int T,
+                                                           int nhead, h16* __restrict__ ctx) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= B * T * nhead) return;
   const int lane = threadIdx.x & 31;
@@ -100,17 +100,17 @@ __global__ void __launch_bounds__(256) prefill_self_kernel(const __nv_bfloat16* 
   load_row32(qkv + (size_t)(b * T + t) * pitch + h * HD, q);
 #pragma unroll
   for (int i = 0; i < HD; ++i) q[i] *= ATT_SCALE;
-  const __nv_bfloat16* kb = qkv + (size_t)b * T * pitch + d + h * HD;
-  const __nv_bfloat16* vb = kb + d;
+  const h16* kb = qkv + (size_t)b * T * pitch + d + h * HD;
+  const h16* vb = kb + d;
   const float o = warp_attend(
       q, t + 1, [&](int j) { return kb + (size_t)j * pitch; }, [&](int j) { return vb + (size_t)j * pitch; }, lane);
-  ctx[(size_t)(b * T + t) * d + h * HD + lane] = __float2bfloat16(o);
+  ctx[(size_t)(b * T + t) * d + h * HD + lane] = to_h16(o);
 }
 
-__global__ void __launch_bounds__(256) cross_kernel(const __nv_bfloat16* __restrict__ q16,
-                                                    const __nv_bfloat16* __restrict__ memkv, int ld_mem, int koff,
+__global__ void __launch_bounds__(256) cross_kernel(const h16* __restrict__ q16,
+                                                    const h16* __restrict__ memkv, int ld_mem, int koff,
                                                     int voff, const int* __restrict__ mem_row, int rows, int T, int S,
-                                                    int nhead, __nv_bfloat16* __restrict__ ctx) {
+                                                    int nhead, h16* __restrict__ ctx) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= rows * nhead) return;
   const int lane = threadIdx.x & 31;
@@ -121,29 +121,29 @@ __global__ void __launch_bounds__(256) cross_kernel(const __nv_bfloat16* __restr
   load_row32(q16 + (size_t)r * d + h * HD, q);
 #pragma unroll
   for (int i = 0; i < HD; ++i) q[i] *= ATT_SCALE;
-  const __nv_bfloat16* kb = memkv + (size_t)img * S * ld_mem + koff + h * HD;
-  const __nv_bfloat16* vb = memkv + (size_t)img * S * ld_mem + voff + h * HD;
+  const h16* kb = memkv + (size_t)img * S * ld_mem + koff + h * HD;
+  const h16* vb = memkv + (size_t)img * S * ld_mem + voff + h * HD;
   const float o = warp_attend(
       q, S, [&](int j) { return kb + (size_t)j * ld_mem; }, [&](int j) { return vb + (size_t)j * ld_mem; }, lane);
-  ctx[(size_t)r * d + h * HD + lane] = __float2bfloat16(o);
+  ctx[(size_t)r * d + h * HD + lane] = to_h16(o);
 }
 
 // ---- single decode step --------------------------------------------------------------------------
-// cache layout: [row][head][tmax][32] bf16 (one layer); the new K/V row is written first, then the
+// cache layout: [row][head][tmax][32] fp16 (one layer); the new K/V row is written first, then the
 // whole warp reads positions 0..t (same-warp global store -> __syncwarp -> load is ordered).
 __global__ void __launch_bounds__(256) self_step_kernel(const DecodeState* __restrict__ state,
-                                                        const __nv_bfloat16* __restrict__ qkv,
-                                                        __nv_bfloat16* kcache, __nv_bfloat16* vcache, int rows,
-                                                        int nhead, int tmax, __nv_bfloat16* __restrict__ ctx) {
+                                                        const h16* __restrict__ qkv,
+                                                        h16* kcache, h16* vcache, int rows,
+                                                        int nhead, int tmax, h16* __restrict__ ctx) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= rows * nhead) return;
   const int lane = threadIdx.x & 31;
   const int h = w % nhead, r = w / nhead;
   const int d = nhead * HD, pitch = 3 * d;
   const int t = state->step;
-  const __nv_bfloat16* row = qkv + (size_t)r * pitch + h * HD;
-  __nv_bfloat16* kb = kcache + ((size_t)r * nhead + h) * tmax * HD;
-  __nv_bfloat16* vb = vcache + ((size_t)r * nhead + h) * tmax * HD;
+  const h16* row = qkv + (size_t)r * pitch + h * HD;
+  h16* kb = kcache + ((size_t)r * nhead + h) * tmax * HD;
+  h16* vb = vcache + ((size_t)r * nhead + h) * tmax * HD;
   kb[(size_t)t * HD + lane] = row[d + lane];
   vb[(size_t)t * HD + lane] = row[2 * d + lane];
   __syncwarp();
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) self_step_kernel(const DecodeState* __res
 #pragma unroll
   for (int i = 0; i < HD; ++i) q[i] *= ATT_SCALE;
   const float o = warp_attend(
-      q, t + 1, [&](int j) { return (const __nv_bfloat16*)(kb + (size_t)j * HD); },
-      [&](int j) { return (const __nv_bfloat16*)(vb + (size_t)j * HD); }, lane);
-  ctx[(size_t)r * d + h * HD + lane] = __float2bfloat16(o);
+      q, t + 1, [&](int j) { return (const h16*)(kb + (size_t)j * HD); },
+      [&](int j) { return (const h16*)(vb + (size_t)j * HD); }, lane);
+  ctx[(size_t)r * d + h * HD + lane] = to_h16(o);
 }
 
 // ---- greedy selection ----------------------------------------------------------------------------
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(DecodeState* state, 
                                                             int eos, uint8_t* __restrict__ finished,
                                                             const float* __restrict__ emb,
                                                             const float* __restrict__ pos, int d, int max_pos,
-                                                            float* __restrict__ x32, __nv_bfloat16* __restrict__ x16,
+                                                            float* __restrict__ x32, h16* __restrict__ x16,
                                                             int rows) {
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(DecodeState* state, 
       const float4 p = *reinterpret_cast<const float4*>(pos + (size_t)(t + 1) * d + c);
       const float4 y = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
       *reinterpret_cast<float4*>(x32 + (size_t)r * d + c) = y;
-      *reinterpret_cast<uint2*>(x16 + (size_t)r * d + c) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      *reinterpret_cast<uint2*>(x16 + (size_t)r * d + c) = make_uint2(pack16(y.x, y.y), pack16(y.z, y.w));
     }
   }
 }
@@ -256,9 +256,9 @@ __global__ void copy_logits_kernel(const float* __restrict__ src, int ld, size_t
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, size_t n, h16* __restrict__ dst) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16(src[i]);
+    dst[i] = to_h16(src[i]);
 }
 
 inline int grid_for(size_t n, int block) {
@@ -271,7 +271,7 @@ inline int grid_for(size_t n, int block) {
 }  // namespace
 
 int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, const float* emb, const float* pos,
-                 int d, int vocab, float* x32, __nv_bfloat16* x16) {
+                 int d, int vocab, float* x32, h16* x16) {
   HM_CHECK(d % 4 == 0, "embed: d_model must be a multiple of 4");
   const int rows = B * T;
   embed_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(tok, ld_tok, rows, T, emb, pos, d, vocab, x32, x16);
@@ -279,15 +279,15 @@ int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, 
   return 0;
 }
 
-int mha_prefill_self(cudaStream_t st, const __nv_bfloat16* qkv16, int B, int T, int nhead, __nv_bfloat16* ctx16) {
+int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16) {
   HM_CHECK(T <= 32 * MAXK, "attention: T=%d exceeds %d", T, 32 * MAXK);
   prefill_self_kernel<<<ceil_div(B * T * nhead, 8), 256, 0, st>>>(qkv16, B, T, nhead, ctx16);
   HM_LAUNCHED();
   return 0;
 }
 
-int mha_prefill_cross(cudaStream_t st, const __nv_bfloat16* q16, const __nv_bfloat16* memkv, int ld_mem, int koff,
-                      int voff, int B, int T, int S, int nhead, __nv_bfloat16* ctx16) {
+int mha_prefill_cross(cudaStream_t st, const h16* q16, const h16* memkv, int ld_mem, int koff,
+                      int voff, int B, int T, int S, int nhead, h16* ctx16) {
   HM_CHECK(S <= 32 * MAXK, "attention: S=%d exceeds %d", S, 32 * MAXK);
   cross_kernel<<<ceil_div(B * T * nhead, 8), 256, 0, st>>>(q16, memkv, ld_mem, koff, voff, nullptr, B * T, T, S, nhead,
                                                           ctx16);
@@ -295,16 +295,16 @@ int mha_prefill_cross(cudaStream_t st, const __nv_bfloat16* q16, const __nv_bflo
   return 0;
 }
 
-int self_attn_step(cudaStream_t st, const DecodeState* state, const __nv_bfloat16* qkv16, __nv_bfloat16* kcache,
-                   __nv_bfloat16* vcache, int rows, int nhead, int tmax, __nv_bfloat16* ctx16) {
+int self_attn_step(cudaStream_t st, const DecodeState* state, const h16* qkv16, h16* kcache,
+                   h16* vcache, int rows, int nhead, int tmax, h16* ctx16) {
   HM_CHECK(tmax <= 32 * MAXK, "attention: max_len=%d exceeds %d", tmax, 32 * MAXK);
   self_step_kernel<<<ceil_div(rows * nhead, 8), 256, 0, st>>>(state, qkv16, kcache, vcache, rows, nhead, tmax, ctx16);
   HM_LAUNCHED();
   return 0;
 }
 
-int cross_attn_step(cudaStream_t st, const __nv_bfloat16* q16, const __nv_bfloat16* memkv, int ld_mem, int koff,
-                    int voff, const int* mem_row, int rows, int S, int nhead, __nv_bfloat16* ctx16) {
+int cross_attn_step(cudaStream_t st, const h16* q16, const h16* memkv, int ld_mem, int koff,
+                    int voff, const int* mem_row, int rows, int S, int nhead, h16* ctx16) {
   cross_kernel<<<ceil_div(rows * nhead, 8), 256, 0, st>>>(q16, memkv, ld_mem, koff, voff, mem_row, rows, 1, S, nhead,
                                                          ctx16);
   HM_LAUNCHED();
@@ -313,7 +313,7 @@ int cross_attn_step(cudaStream_t st, const __nv_bfloat16* q16, const __nv_bfloat
 
 int greedy_select(cudaStream_t st, DecodeState* state, const float* logits, int ld, int n_valid, int rows,
                   int64_t* tokens, int ld_tok, float* logprob, int max_len, int eos, uint8_t* finished,
-                  const float* emb, const float* pos, int d, int max_pos, float* x32, __nv_bfloat16* x16) {
+                  const float* emb, const float* pos, int d, int max_pos, float* x32, h16* x16) {
   greedy_select_kernel<<<rows, 256, 0, st>>>(state, logits, ld, n_valid, tokens, ld_tok, logprob, max_len, eos,
                                              finished, emb, pos, d, max_pos, x32, x16, rows);
   HM_LAUNCHED();
@@ -349,8 +349,8 @@ int copy_logits(cudaStream_t st, const float* src, int ld, int rows, int n_valid
   return 0;
 }
 
-int f32_to_bf16(cudaStream_t st, const float* src, size_t n, __nv_bfloat16* dst) {
-  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, dst);
+int f32_to_f16(cudaStream_t st, const float* src, size_t n, h16* dst) {
+  f32_to_f16_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, dst);
   HM_LAUNCHED();
   return 0;
 }

@@ -40,7 +40,7 @@ struct HostTensor {
 };
 
 struct Lin {
-  __nv_bfloat16* w = nullptr;   // [n, k] bf16 (n padded to a multiple of 32 with zero rows)
+  h16* w = nullptr;   // [n, k] fp16 (n padded to a multiple of 32 with zero rows)
   float* b = nullptr;           // [n] fp32 or nullptr
   int n = 0, k = 0;
 };
@@ -146,6 +146,9 @@ int need(hmocr_engine* e, const std::string& key, std::vector<int64_t> shape, co
   return 0;
 }
 
+// host-side fp32 -> fp16, saturating like the device conversions
+inline h16 host_to_h16(float v) { return __float2half(v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v)); }
+
 int upload_f32(hmocr_engine* e, const float* src, size_t n, float** out) {
   void* p;
   HM_TRY(arena_alloc(e, n * sizeof(float), &p));
@@ -165,15 +168,15 @@ int upload_norm(hmocr_engine* e, const std::string& prefix, int64_t n, Norm* out
   return upload_vec(e, prefix + ".bias", n, &out->b);
 }
 
-// rows [r0, r0+rows) of a [*, k] fp32 matrix -> bf16 [npad, k] (zero padded), bias likewise
+// rows [r0, r0+rows) of a [*, k] fp32 matrix -> fp16 [npad, k] (zero padded), bias likewise
 int upload_lin_rows(hmocr_engine* e, const float* w, const float* b, int rows, int k, Lin* out) {
   const int npad = (rows + 31) / 32 * 32;
-  std::vector<__nv_bfloat16> tmp((size_t)npad * k, __float2bfloat16(0.f));
-  for (size_t i = 0; i < (size_t)rows * k; ++i) tmp[i] = __float2bfloat16(w[i]);
+  std::vector<h16> tmp((size_t)npad * k, host_to_h16(0.f));
+  for (size_t i = 0; i < (size_t)rows * k; ++i) tmp[i] = host_to_h16(w[i]);
   void* p;
   HM_TRY(arena_alloc(e, tmp.size() * 2, &p));
   HM_CUDA(cudaMemcpy(p, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
-  out->w = reinterpret_cast<__nv_bfloat16*>(p);
+  out->w = reinterpret_cast<h16*>(p);
   out->n = npad;
   out->k = k;
   out->b = nullptr;
@@ -192,18 +195,18 @@ int upload_lin(hmocr_engine* e, const std::string& prefix, int n, int k, bool bi
   return upload_lin_rows(e, w->f.data(), b ? b->f.data() : nullptr, n, k, out);
 }
 
-int run_lin(cudaStream_t st, const __nv_bfloat16* a, int lda, int M, const Lin& l, GemmEpilogue epi) {
+int run_lin(cudaStream_t st, const h16* a, int lda, int M, const Lin& l, GemmEpilogue epi) {
   epi.bias = l.b;
-  return gemm_bf16(st, a, lda, M, l.k, l.w, l.n, epi);
+  return gemm_f16(st, a, lda, M, l.k, l.w, l.n, epi);
 }
 
 // ------------------------------------------------------------------------------------------------
 // encoder schedule            /root/reference/src/model_swin.py:39-46 over swin_t.features
 // ------------------------------------------------------------------------------------------------
-int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, __nv_bfloat16* enc16, cudaStream_t st) {
+int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* enc16, cudaStream_t st) {
   const size_t tok1 = (size_t)B * 24 * 80;
   float *xa, *xb;
-  __nv_bfloat16 *xn, *qkv, *ctx, *hid;
+  h16 *xn, *qkv, *ctx, *hid;
   HM_TRY(ws_get(e, "enc.xa", tok1 * 96, &xa));
   HM_TRY(ws_get(e, "enc.xb", tok1 * 96 / 2, &xb));
   HM_TRY(ws_get(e, "enc.xn", tok1 * 96, &xn));
@@ -221,7 +224,7 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, __nv_
       const SwinBlock& sb = e->blocks[blk];
       HM_TRY(layernorm(st, x, rows, C, sb.n1.g, sb.n1.b, xn, nullptr));
       GemmEpilogue eq;
-      eq.out_bf16 = qkv; eq.ld16 = 3 * C;
+      eq.out_f16 = qkv; eq.ld16 = 3 * C;
       HM_TRY(run_lin(st, xn, C, rows, sb.qkv, eq));
       HM_TRY(window_attention(st, qkv, sb.qkv.b, sb.rel_bias, B, H, W, C, HEADS[s], (j & 1) ? 3 : 0, ctx));
       GemmEpilogue ep;
@@ -229,7 +232,7 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, __nv_
       HM_TRY(run_lin(st, ctx, C, rows, sb.proj, ep));
       HM_TRY(layernorm(st, x, rows, C, sb.n2.g, sb.n2.b, xn, nullptr));
       GemmEpilogue e1;
-      e1.act = 1; e1.out_bf16 = hid; e1.ld16 = 4 * C;
+      e1.act = 1; e1.out_f16 = hid; e1.ld16 = 4 * C;
       HM_TRY(run_lin(st, xn, C, rows, sb.fc1, e1));
       GemmEpilogue e2;
       e2.residual = x; e2.ldr = C; e2.out_f32 = x; e2.ld32 = C;
@@ -247,24 +250,24 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, __nv_
     }
   }
   const int rows = B * MEM_S;
-  HM_TRY(f32_to_bf16(st, x, (size_t)rows * SWIN_OUT, xn));
+  HM_TRY(f32_to_f16(st, x, (size_t)rows * SWIN_OUT, xn));
   GemmEpilogue eo;
   eo.out_f32 = enc32; eo.ld32 = e->cfg.d_model;
-  eo.out_bf16 = enc16; eo.ld16 = e->cfg.d_model;
+  eo.out_f16 = enc16; eo.ld16 = e->cfg.d_model;
   HM_TRY(run_lin(st, xn, SWIN_OUT, rows, e->proj, eo));
   return 0;
 }
 
 // memory K/V of all layers in one GEMM: memkv[b*S+s, l*2d + {0..d-1: K, d..2d-1: V}]
-int project_memory(hmocr_engine* e, const __nv_bfloat16* enc16, int B, __nv_bfloat16* memkv, cudaStream_t st) {
+int project_memory(hmocr_engine* e, const h16* enc16, int B, h16* memkv, cudaStream_t st) {
   GemmEpilogue ek;
-  ek.out_bf16 = memkv; ek.ld16 = e->ca_kv.n;
+  ek.out_f16 = memkv; ek.ld16 = e->ca_kv.n;
   return run_lin(st, enc16, e->cfg.d_model, B * MEM_S, e->ca_kv, ek);
 }
 
 struct DecBufs {
   float* x32;
-  __nv_bfloat16 *x16, *qkv, *q, *ctx, *hid;
+  h16 *x16, *qkv, *q, *ctx, *hid;
   float* logits;
 };
 
@@ -282,29 +285,29 @@ int dec_bufs(hmocr_engine* e, const char* tag, size_t rows, DecBufs* b) {
 }
 
 // everything of one decoder layer after the self-attention context is in b.ctx
-int layer_tail(hmocr_engine* e, const DecLayer& L, int l, const DecBufs& b, int rows, const __nv_bfloat16* memkv,
+int layer_tail(hmocr_engine* e, const DecLayer& L, int l, const DecBufs& b, int rows, const h16* memkv,
                const int* mem_row, int T, cudaStream_t st) {
   const int d = e->cfg.d_model, ff = e->cfg.dim_feedforward, nh = e->cfg.nhead;
   GemmEpilogue e1;                       // x = LN1(x + out_proj(ctx))
-  e1.residual = b.x32; e1.ldr = d; e1.out_f32 = b.x32; e1.ld32 = d; e1.out_bf16 = b.x16; e1.ld16 = d;
+  e1.residual = b.x32; e1.ldr = d; e1.out_f32 = b.x32; e1.ld32 = d; e1.out_f16 = b.x16; e1.ld16 = d;
   e1.ln_gamma = L.n1.g; e1.ln_beta = L.n1.b;
   HM_TRY(run_lin(st, b.ctx, d, rows, L.sa_out, e1));
   GemmEpilogue eq;
-  eq.out_bf16 = b.q; eq.ld16 = d;
+  eq.out_f16 = b.q; eq.ld16 = d;
   HM_TRY(run_lin(st, b.x16, d, rows, L.ca_q, eq));
   if (T > 0)
     HM_TRY(mha_prefill_cross(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, rows / T, T, MEM_S, nh, b.ctx));
   else
     HM_TRY(cross_attn_step(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, mem_row, rows, MEM_S, nh, b.ctx));
   GemmEpilogue e2;                       // x = LN2(x + out_proj(ctx))
-  e2.residual = b.x32; e2.ldr = d; e2.out_f32 = b.x32; e2.ld32 = d; e2.out_bf16 = b.x16; e2.ld16 = d;
+  e2.residual = b.x32; e2.ldr = d; e2.out_f32 = b.x32; e2.ld32 = d; e2.out_f16 = b.x16; e2.ld16 = d;
   e2.ln_gamma = L.n2.g; e2.ln_beta = L.n2.b;
   HM_TRY(run_lin(st, b.ctx, d, rows, L.ca_out, e2));
   GemmEpilogue ef;
-  ef.act = 2; ef.out_bf16 = b.hid; ef.ld16 = ff;
+  ef.act = 2; ef.out_f16 = b.hid; ef.ld16 = ff;
   HM_TRY(run_lin(st, b.x16, d, rows, L.l1, ef));
   GemmEpilogue e3;                       // x = LN3(x + linear2(relu(linear1 x)))
-  e3.residual = b.x32; e3.ldr = d; e3.out_f32 = b.x32; e3.ld32 = d; e3.out_bf16 = b.x16; e3.ld16 = d;
+  e3.residual = b.x32; e3.ldr = d; e3.out_f32 = b.x32; e3.ld32 = d; e3.out_f16 = b.x16; e3.ld16 = d;
   e3.ln_gamma = L.n3.g; e3.ln_beta = L.n3.b;
   HM_TRY(run_lin(st, b.hid, ff, rows, L.l2, e3));
   return 0;
@@ -317,18 +320,18 @@ int decoder_forward_impl(hmocr_engine* e, const float* enc32, const int64_t* tgt
                          cudaStream_t st) {
   const int d = e->cfg.d_model, nh = e->cfg.nhead;
   const int rows = B * T;
-  __nv_bfloat16 *enc16, *memkv;
+  h16 *enc16, *memkv;
   HM_TRY(ws_get(e, "tf.enc16", (size_t)B * MEM_S * d, &enc16));
   HM_TRY(ws_get(e, "tf.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
   DecBufs b;
   HM_TRY(dec_bufs(e, "tf", rows, &b));
-  HM_TRY(f32_to_bf16(st, enc32, (size_t)B * MEM_S * d, enc16));
+  HM_TRY(f32_to_f16(st, enc32, (size_t)B * MEM_S * d, enc16));
   HM_TRY(project_memory(e, enc16, B, memkv, st));
   HM_TRY(embed_tokens(st, tgt, T, B, T, e->emb, e->pos, d, e->cfg.vocab_size, b.x32, b.x16));
   for (int l = 0; l < e->cfg.num_layers; ++l) {
     const DecLayer& L = e->layers[l];
     GemmEpilogue ei;
-    ei.out_bf16 = b.qkv; ei.ld16 = 3 * d;
+    ei.out_f16 = b.qkv; ei.ld16 = 3 * d;
     HM_TRY(run_lin(st, b.x16, d, rows, L.sa_in, ei));
     HM_TRY(mha_prefill_self(st, b.qkv, B, T, nh, b.ctx));
     HM_TRY(layer_tail(e, L, l, b, rows, memkv, nullptr, T, st));
@@ -345,20 +348,20 @@ int decoder_forward_impl(hmocr_engine* e, const float* enc32, const int64_t* tgt
 // ------------------------------------------------------------------------------------------------
 struct GenBufs {
   DecBufs b;
-  __nv_bfloat16 *kcache, *vcache;   // [L][rows][nhead][tmax][32]
+  h16 *kcache, *vcache;   // [L][rows][nhead][tmax][32]
   DecodeState* state;
   uint8_t* finished;
   int tmax;
 };
 
-int enqueue_step(hmocr_engine* e, const GenBufs& g, int rows, const __nv_bfloat16* memkv, int64_t* tokens,
+int enqueue_step(hmocr_engine* e, const GenBufs& g, int rows, const h16* memkv, int64_t* tokens,
                  float* logprob, int max_len, cudaStream_t st) {
   const int d = e->cfg.d_model, nh = e->cfg.nhead;
   const size_t layer_stride = (size_t)rows * nh * g.tmax * 32;
   for (int l = 0; l < e->cfg.num_layers; ++l) {
     const DecLayer& L = e->layers[l];
     GemmEpilogue ei;
-    ei.out_bf16 = g.b.qkv; ei.ld16 = 3 * d;
+    ei.out_f16 = g.b.qkv; ei.ld16 = 3 * d;
     HM_TRY(run_lin(st, g.b.x16, d, rows, L.sa_in, ei));
     HM_TRY(self_attn_step(st, g.state, g.b.qkv, g.kcache + l * layer_stride, g.vcache + l * layer_stride, rows, nh,
                           g.tmax, g.b.ctx));
@@ -373,10 +376,10 @@ int enqueue_step(hmocr_engine* e, const GenBufs& g, int rows, const __nv_bfloat1
   return 0;
 }
 
-int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int64_t* tokens,
+int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, int64_t* tokens,
                         float* logprob, int32_t* steps, cudaStream_t st);
 
-int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int beam,
+int generate_from_memory_impl(hmocr_engine* e, const h16* enc16, int B, int max_len, int beam,
                               int64_t* tokens, float* logprob, int32_t* steps, float* score, cudaStream_t st) {
   HM_CHECK(beam == 1, "beam search (beam=%d) is not built yet in this round: only greedy (beam=1)", beam);
   HM_CHECK(max_len >= 1 && max_len <= e->cfg.max_seq_len,
@@ -385,7 +388,7 @@ int generate_from_memory_impl(hmocr_engine* e, const __nv_bfloat16* enc16, int B
   if (e->decode_impl == 0) return generate_persistent(e, enc16, B, max_len, tokens, logprob, steps, st);
   const int d = e->cfg.d_model, nh = e->cfg.nhead, L = e->cfg.num_layers;
   const int rows = B;
-  __nv_bfloat16* memkv;
+  h16* memkv;
   HM_TRY(ws_get(e, "gen.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
   GenBufs g;
   g.tmax = e->cfg.max_seq_len;
@@ -462,9 +465,7 @@ void pack_chunk(std::vector<__half>& dst, size_t off, const float* w, const floa
   for (int r = 0; r < DP_CH_ROWS; ++r) {
     for (int k = 0; k < 264; ++k) {
       const bool ok = (k < 256) && (row0 + r < valid_rows);
-      float v = ok ? w[(size_t)(row0 + r) * K + col0 + k] : 0.f;
-      v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
-      dst[off + (size_t)r * 264 + k] = __float2half(v);
+      dst[off + (size_t)r * 264 + k] = host_to_h16(ok ? w[(size_t)(row0 + r) * K + col0 + k] : 0.f);
     }
     const float b = (bias != nullptr && row0 + r < valid_rows) ? bias[row0 + r] : 0.f;
     memcpy(&dst[off + (size_t)r * 264 + 256], &b, sizeof(float));
@@ -537,7 +538,7 @@ int pack_decode_operands(hmocr_engine* e) {
 
 // greedy decode with the persistent cluster kernel: a few launches of `steps_per_launch` steps, the
 // host only polls the all-finished flag of the PREVIOUS launch (the GPU never idles)
-int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int max_len, int64_t* tokens,
+int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, int64_t* tokens,
                         float* logprob, int32_t* steps, cudaStream_t st) {
   const int nh = e->cfg.nhead, L = e->cfg.num_layers, rows = B;
   float* memkv;                       // memory K/V of all layers, fp32 out of the GEMM, fp16 after the repack
@@ -603,7 +604,7 @@ int generate_persistent(hmocr_engine* e, const __nv_bfloat16* enc16, int B, int 
 int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int beam, int64_t* tokens, float* logprob,
                   int32_t* steps, float* score, cudaStream_t st) {
   float* enc32;
-  __nv_bfloat16* enc16;
+  h16* enc16;
   HM_TRY(ws_get(e, "gen.enc32", (size_t)B * MEM_S * e->cfg.d_model, &enc32));
   HM_TRY(ws_get(e, "gen.enc16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
   HM_CUDA(cudaEventRecord(e->ev[0], st));
@@ -826,7 +827,7 @@ HM_API int hmocr_read_trace(hmocr_engine* e, int64_t* out_host, int n) {
 HM_API int hmocr_encode(hmocr_engine* e, const float* images, int B, float* enc_out, void* stream) {
   HM_TRY(check_ready(e, B));
   HM_CHECK(images != nullptr && enc_out != nullptr, "hmocr_encode: null buffer");
-  __nv_bfloat16* enc16;
+  h16* enc16;
   HM_TRY(ws_get(e, "enc.out16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
   return encode_impl(e, images, B, enc_out, enc16, static_cast<cudaStream_t>(stream));
 }
@@ -852,9 +853,9 @@ HM_API int hmocr_generate_from_memory(hmocr_engine* e, const float* enc_out, int
   HM_TRY(check_ready(e, B));
   HM_CHECK(enc_out != nullptr && tokens != nullptr, "hmocr_generate_from_memory: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  __nv_bfloat16* enc16;
+  h16* enc16;
   HM_TRY(ws_get(e, "gen.enc16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
-  HM_TRY(f32_to_bf16(st, enc_out, (size_t)B * MEM_S * e->cfg.d_model, enc16));
+  HM_TRY(f32_to_f16(st, enc_out, (size_t)B * MEM_S * e->cfg.d_model, enc16));
   HM_CUDA(cudaEventRecord(e->ev[0], st));
   HM_CUDA(cudaEventRecord(e->ev[1], st));
   HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));
@@ -903,21 +904,21 @@ HM_API int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_
 }
 
 // ---- kernel-level exports ----------------------------------------------------------------------------
-HM_API int hmocr_gemm_bf16(const void* a, int lda, int M, int K, const void* w, int N, const float* bias, int act,
-                           const float* residual, int ldr, float* out_f32, int ld32, void* out_bf16, int ld16,
+HM_API int hmocr_gemm_f16(const void* a, int lda, int M, int K, const void* w, int N, const float* bias, int act,
+                           const float* residual, int ldr, float* out_f32, int ld32, void* out_f16, int ld16,
                            const float* ln_gamma, const float* ln_beta, int force_bn, void* stream) {
   GemmEpilogue epi;
   epi.bias = bias; epi.act = act; epi.residual = residual; epi.ldr = ldr;
   epi.out_f32 = out_f32; epi.ld32 = ld32;
-  epi.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); epi.ld16 = ld16;
+  epi.out_f16 = static_cast<h16*>(out_f16); epi.ld16 = ld16;
   epi.ln_gamma = ln_gamma; epi.ln_beta = ln_beta;
-  return gemm_bf16(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), lda, M, K,
-                   static_cast<const __nv_bfloat16*>(w), N, epi, force_bn);
+  return gemm_f16(static_cast<cudaStream_t>(stream), static_cast<const h16*>(a), lda, M, K,
+                   static_cast<const h16*>(w), N, epi, force_bn);
 }
 
-HM_API int hmocr_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, void* out_bf16,
+HM_API int hmocr_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, void* out_f16,
                            float* out_f32, void* stream) {
-  return layernorm(static_cast<cudaStream_t>(stream), x, rows, C, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16),
+  return layernorm(static_cast<cudaStream_t>(stream), x, rows, C, gamma, beta, static_cast<h16*>(out_f16),
                    out_f32);
 }
 
@@ -927,13 +928,13 @@ HM_API int hmocr_patch_embed(const float* images, int B, const float* w, const f
 }
 
 HM_API int hmocr_patch_merge_ln(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
-                                void* out_bf16, void* stream) {
+                                void* out_f16, void* stream) {
   return patch_merge_ln(static_cast<cudaStream_t>(stream), x, B, H, W, C, gamma, beta,
-                        static_cast<__nv_bfloat16*>(out_bf16));
+                        static_cast<h16*>(out_f16));
 }
 
 HM_API int hmocr_window_attention(const void* qkv, const float* qkv_bias, const float* rel_bias, int B, int H, int W,
                                   int C, int heads, int shift, void* ctx, void* stream) {
-  return window_attention(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv), qkv_bias,
-                          rel_bias, B, H, W, C, heads, shift, static_cast<__nv_bfloat16*>(ctx));
+  return window_attention(static_cast<cudaStream_t>(stream), static_cast<const h16*>(qkv), qkv_bias,
+                          rel_bias, B, H, W, C, heads, shift, static_cast<h16*>(ctx));
 }

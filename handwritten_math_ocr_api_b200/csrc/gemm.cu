@@ -1,6 +1,6 @@
 // Persistent warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   C[M,N] = epilogue( A[M,K] x W[N,K]^T )      A, W bf16 (K contiguous), fp32 accumulation in TMEM
+//   C[M,N] = epilogue( A[M,K] x W[N,K]^T )      A, W fp16 (K contiguous), fp32 accumulation in TMEM
 //
 // Replaces every nn.Linear on the hot path (torchvision swin_transformer.py:179,215,444,85;
 // /root/reference/src/model_swin.py:45,64,87; torch MultiheadAttention in/out projections,
@@ -12,7 +12,7 @@
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
 //              tcgen05.commit releases the ring slot ("empty") and publishes the accumulator
 //   warps 2-9  epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per
-//              thread), fuse bias / GELU / ReLU / fp32 residual / LayerNorm, store fp32 and/or bf16.
+//              thread), fuse bias / GELU / ReLU / fp32 residual / LayerNorm, store fp32 and/or fp16.
 //              A warp may only touch TMEM lanes [32*(warp%4), +32), so two warps share each lane
 //              quarter and take alternate 32-column chunks: the small-K GEMMs of Swin stage 1/2 are
 //              epilogue-bound, and one epilogue warp per scheduler cannot hide its own latencies.
@@ -65,8 +65,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 template <int BN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4)                 // D format  = F32
-         | (1u << 7)               // A format  = BF16
-         | (1u << 10)              // B format  = BF16
+         | (0u << 7)               // A format  = F16
+         | (0u << 10)              // B format  = F16
          | (uint32_t(BN >> 3) << 17)   // N
          | (uint32_t(BM >> 4) << 24);  // M
 }
@@ -111,12 +111,12 @@ __device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t t
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
-      if (e.out_bf16 != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ld16 + col);
+      if (e.out_f16 != nullptr) {
+        uint4* o = reinterpret_cast<uint4*>(e.out_f16 + (size_t)row * e.ld16 + col);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          o[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                            pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+          o[q] = make_uint4(pack16(v[8 * q], v[8 * q + 1]), pack16(v[8 * q + 2], v[8 * q + 3]),
+                            pack16(v[8 * q + 4], v[8 * q + 5]), pack16(v[8 * q + 6], v[8 * q + 7]));
       }
     }
   }
@@ -184,12 +184,12 @@ __device__ __forceinline__ void epilogue_ln(const GemmEpilogue& e, uint32_t tadd
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
-      if (e.out_bf16 != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ld16 + col);
+      if (e.out_f16 != nullptr) {
+        uint4* o = reinterpret_cast<uint4*>(e.out_f16 + (size_t)row * e.ld16 + col);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          o[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                            pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+          o[q] = make_uint4(pack16(v[8 * q], v[8 * q + 1]), pack16(v[8 * q + 2], v[8 * q + 3]),
+                            pack16(v[8 * q + 4], v[8 * q + 5]), pack16(v[8 * q + 6], v[8 * q + 7]));
       }
     }
   }
@@ -269,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t bbase = abase + C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, make_smem_desc(abase + k * 32), make_smem_desc(bbase + k * 32), idesc,
+            umma_f16(d_tmem, make_smem_desc(abase + k * 32), make_smem_desc(bbase + k * 32), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
@@ -335,7 +335,7 @@ int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CU
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d", (int)r,
@@ -347,7 +347,7 @@ int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CU
 }
 
 template <int BN>
-int launch(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W, int N,
+int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* W, int N,
            const GemmEpilogue& epi) {
   using C = Cfg<BN>;
   alignas(64) CUtensorMap tmA, tmB;
@@ -390,7 +390,7 @@ int gemm_init() {
   return 0;
 }
 
-int gemm_bf16(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W, int N,
+int gemm_f16(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* W, int N,
               const GemmEpilogue& epi, int force_bn) {
   HM_TRY(gemm_init());
   HM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -398,9 +398,9 @@ int gemm_bf16(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K
   HM_CHECK(K % 8 == 0 && lda % 8 == 0, "gemm: K=%d and lda=%d must be multiples of 8", K, lda);
   HM_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
            "gemm: operands must be 16-byte aligned");
-  HM_CHECK(epi.out_f32 != nullptr || epi.out_bf16 != nullptr, "gemm: no output");
+  HM_CHECK(epi.out_f32 != nullptr || epi.out_f16 != nullptr, "gemm: no output");
   HM_CHECK(epi.out_f32 == nullptr || epi.ld32 % 4 == 0, "gemm: ld32 must be a multiple of 4");
-  HM_CHECK(epi.out_bf16 == nullptr || epi.ld16 % 8 == 0, "gemm: ld16 must be a multiple of 8");
+  HM_CHECK(epi.out_f16 == nullptr || epi.ld16 % 8 == 0, "gemm: ld16 must be a multiple of 8");
   HM_CHECK(epi.residual == nullptr || epi.ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
   int bn = force_bn;
   if (epi.ln_gamma != nullptr) {

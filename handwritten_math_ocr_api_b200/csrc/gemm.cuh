@@ -1,4 +1,4 @@
-// tcgen05 GEMM with fused epilogues:  C[M,N] = epi( A[M,K] (bf16, K-major) x W[N,K]^T (bf16) )
+// tcgen05 GEMM with fused epilogues:  C[M,N] = epi( A[M,K] (fp16, K-major) x W[N,K]^T (fp16) )
 #pragma once
 #include "common.cuh"
 
@@ -11,7 +11,7 @@ struct GemmEpilogue {
   int ldr = 0;
   float* out_f32 = nullptr;           // fp32 [M, ld32]
   int ld32 = 0;
-  __nv_bfloat16* out_bf16 = nullptr;  // bf16 [M, ld16]
+  h16* out_f16 = nullptr;  // fp16 [M, ld16]
   int ld16 = 0;
   // LayerNorm over the N axis applied after bias/act/residual; needs N == tile width
   // (N in {64,96,128,192,256}).  Outputs then hold the normalised rows.
@@ -19,9 +19,9 @@ struct GemmEpilogue {
   const float* ln_beta = nullptr;
 };
 
-// A: bf16 [M, K] with row pitch lda (elements); W: bf16 [N, K] contiguous.
+// A: fp16 [M, K] with row pitch lda (elements); W: fp16 [N, K] contiguous.
 // Requirements: N % 32 == 0 (pad the weight), lda % 8 == 0, K % 8 == 0, 16-byte aligned pointers.
-int gemm_bf16(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W,
+int gemm_f16(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* W,
               int N, const GemmEpilogue& epi, int force_bn = 0);
 
 int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent

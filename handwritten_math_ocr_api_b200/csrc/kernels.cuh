@@ -6,15 +6,15 @@ namespace hmocr {
 
 // ---- Swin encoder ------------------------------------------------------------------------------
 int layernorm(cudaStream_t st, const float* x, int rows, int C, const float* gamma, const float* beta,
-              __nv_bfloat16* out16, float* out32);
+              h16* out16, float* out32);
 int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin, const float* gamma,
-                   const float* beta, __nv_bfloat16* out16);
+                   const float* beta, h16* out16);
 int patch_embed(cudaStream_t st, const float* images, int B, const float* w, const float* b, const float* g,
                 const float* beta, float* x);
-int window_attention(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
-                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx);       // tensor-core (swin_attention.cu)
-int window_attention_fp32(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias,
-                          int B, int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx);   // CUDA-core reference
+int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
+                     int H, int W, int C, int heads, int shift, h16* ctx);       // tensor-core (swin_attention.cu)
+int window_attention_fp32(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias,
+                          int B, int H, int W, int C, int heads, int shift, h16* ctx);   // CUDA-core reference
 
 // ---- decoder -------------------------------------------------------------------------------------
 struct DecodeState {      // device-resident control block of one generate call
@@ -26,28 +26,28 @@ struct DecodeState {      // device-resident control block of one generate call
 
 // x[r] = embedding[tok[b, t]] + pos[t]  for r = b*T + t   (src/model_swin.py:73-75)
 int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, const float* emb, const float* pos,
-                 int d, int vocab, float* x32, __nv_bfloat16* x16);
+                 int d, int vocab, float* x32, h16* x16);
 
 // teacher-forced attention over a [B*T, ...] activation buffer: one warp per (b, head, query)
 //   self : q,k,v = columns [0,d),[d,2d),[2d,3d) of qkv16 (row pitch 3d), causal
 //   cross: q from q16 (pitch d); k,v from memkv (row (b*S+s), pitch ld_mem, column offsets koff/voff)
-int mha_prefill_self(cudaStream_t st, const __nv_bfloat16* qkv16, int B, int T, int nhead, __nv_bfloat16* ctx16);
-int mha_prefill_cross(cudaStream_t st, const __nv_bfloat16* q16, const __nv_bfloat16* memkv, int ld_mem, int koff,
-                      int voff, int B, int T, int S, int nhead, __nv_bfloat16* ctx16);
+int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16);
+int mha_prefill_cross(cudaStream_t st, const h16* q16, const h16* memkv, int ld_mem, int koff,
+                      int voff, int B, int T, int S, int nhead, h16* ctx16);
 
 // one decode step, one warp per (row, head).  `mem_row` maps a decode row to its image (beam search:
 // several hypotheses share one image's memory K/V); nullptr = identity.
-int self_attn_step(cudaStream_t st, const DecodeState* state, const __nv_bfloat16* qkv16, __nv_bfloat16* kcache,
-                   __nv_bfloat16* vcache, int rows, int nhead, int tmax, __nv_bfloat16* ctx16);
-int cross_attn_step(cudaStream_t st, const __nv_bfloat16* q16, const __nv_bfloat16* memkv, int ld_mem, int koff,
-                    int voff, const int* mem_row, int rows, int S, int nhead, __nv_bfloat16* ctx16);
+int self_attn_step(cudaStream_t st, const DecodeState* state, const h16* qkv16, h16* kcache,
+                   h16* vcache, int rows, int nhead, int tmax, h16* ctx16);
+int cross_attn_step(cudaStream_t st, const h16* q16, const h16* memkv, int ld_mem, int koff,
+                    int voff, const int* mem_row, int rows, int S, int nhead, h16* ctx16);
 
 // greedy head: argmax (first max) + log-softmax of the winner over logits[rows, ld] (n_valid
 // columns), append to tokens[:, t+1], update finished bookkeeping, and embed the chosen token
 // for step t+1 (src/inference.py:20-24 + src/model_swin.py:73-75).
 int greedy_select(cudaStream_t st, DecodeState* state, const float* logits, int ld, int n_valid, int rows,
                   int64_t* tokens, int ld_tok, float* logprob, int max_len, int eos, uint8_t* finished,
-                  const float* emb, const float* pos, int d, int max_pos, float* x32, __nv_bfloat16* x16);
+                  const float* emb, const float* pos, int d, int max_pos, float* x32, h16* x16);
 int advance_step(cudaStream_t st, DecodeState* state);
 int init_decode(cudaStream_t st, DecodeState* state, int64_t* tokens, int ld_tok, int rows, int sos, int pad,
                 uint8_t* finished, float* logprob, int max_len);
@@ -57,6 +57,6 @@ int finalize_decode(cudaStream_t st, const DecodeState* state, int64_t* tokens, 
 
 // misc
 int copy_logits(cudaStream_t st, const float* src, int ld, int rows, int n_valid, float* dst);
-int f32_to_bf16(cudaStream_t st, const float* src, size_t n, __nv_bfloat16* dst);
+int f32_to_f16(cudaStream_t st, const float* src, size_t n, h16* dst);
 
 }  // namespace hmocr

@@ -5,7 +5,7 @@
 //   * the cyclic shift, zero padding, window partition and their inverses are index arithmetic on
 //     the un-shifted, un-padded qkv buffer (rolled position (r,c) reads padded position
 //     ((r+sh)%Hp, (c+sw)%Wp)); a padded token has q = k = v = qkv.bias; its output is never written;
-//   * Q, K, V rows (49 x 32 bf16 each) are gathered with 16-byte cp.async into padded 64x40 tiles;
+//   * Q, K, V rows (49 x 32 fp16 each) are gathered with 16-byte cp.async into padded 64x40 tiles;
 //   * S = Q K^T (mma.sync m16n8k16, 4 m-tiles x 7 n-tiles x 2 k-steps), scaled by 32^-0.5, plus bias,
 //     plus the -100 region mask; softmax in fp32 registers with quad shuffles;
 //   * O = P V with P re-packed from the S accumulators straight into A fragments and V read through
@@ -19,14 +19,14 @@ namespace hmocr {
 namespace {
 
 constexpr int WS = 7, WN = 49, HD = 32;
-constexpr int TP = 40;            // tile pitch (bf16): 80-byte rows are conflict-free for ldmatrix
+constexpr int TP = 40;            // tile pitch (fp16): 80-byte rows are conflict-free for ldmatrix
 constexpr int BP = 52;            // bias pitch (fp32)
 constexpr int WARPS = 4;
 
 struct WarpTile {
-  __nv_bfloat16 q[64][TP];
-  __nv_bfloat16 k[64][TP];
-  __nv_bfloat16 v[64][TP];
+  h16 q[64][TP];
+  h16 k[64][TP];
+  h16 v[64][TP];
   float bias[WN][BP];
   int tok[64];       // token row in the qkv buffer, -1 if padded
   int region[64];
@@ -45,7 +45,7 @@ __device__ __forceinline__ void ldsm2_trans(uint32_t addr, uint32_t (&r)[2]) {
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
       "{%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -54,11 +54,11 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* __restrict__ qkv,
                                                                      const float* __restrict__ qkv_bias,
                                                                      const float* __restrict__ rel_bias, int B, int H,
                                                                      int W, int C, int heads, int sh, int sw, int Hp,
-                                                                     int Wp, __nv_bfloat16* __restrict__ ctx) {
+                                                                     int Wp, h16* __restrict__ ctx) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpTile& s = reinterpret_cast<WarpTile*>(smem_raw)[warp];
@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_
   // one-time: zero the padding rows (finite operands for the masked / zero-probability lanes) and
   // fetch this head's relative-position bias
   for (int i = lane; i < 15 * TP; i += 32) {
-    (&s.k[WN][0])[i] = __float2bfloat16(0.f);
-    (&s.v[WN][0])[i] = __float2bfloat16(0.f);
-    (&s.q[WN][0])[i] = __float2bfloat16(0.f);
+    (&s.k[WN][0])[i] = to_h16(0.f);
+    (&s.v[WN][0])[i] = to_h16(0.f);
+    (&s.q[WN][0])[i] = to_h16(0.f);
   }
   for (int i = lane; i < WN * WN; i += 32) s.bias[i / WN][i % WN] = __ldg(rel_bias + (size_t)h * WN * WN + i);
   __syncwarp();
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_
     __syncwarp();
     for (int i = lane; i < WN * 12; i += 32) {
       const int p = i / 12, m = (i % 12) >> 2, ch = i & 3;
-      __nv_bfloat16* dst = (m == 0 ? &s.q[p][0] : (m == 1 ? &s.k[p][0] : &s.v[p][0])) + ch * 8;
+      h16* dst = (m == 0 ? &s.q[p][0] : (m == 1 ? &s.k[p][0] : &s.v[p][0])) + ch * 8;
       const int col = m * C + h * HD + ch * 8;
       const int tok = s.tok[p];
       if (tok >= 0) {
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_
         const float4 a = __ldg(reinterpret_cast<const float4*>(qkv_bias + col));
         const float4 c4 = __ldg(reinterpret_cast<const float4*>(qkv_bias + col + 4));
         *reinterpret_cast<uint4*>(dst) =
-            make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c4.x, c4.y), pack_bf16(c4.z, c4.w));
+            make_uint4(pack16(a.x, a.y), pack16(a.z, a.w), pack16(c4.x, c4.y), pack16(c4.z, c4.w));
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_
         const float p0 = __expf(sc[nt][0] - mx0), p1 = __expf(sc[nt][1] - mx0);
         const float p2 = __expf(sc[nt][2] - mx1), p3 = __expf(sc[nt][3] - mx1);
         sum0 += p0 + p1; sum1 += p2 + p3;
-        pa[nt >> 1][(nt & 1) * 2] = pack_bf16(p0, p1);        // row g4   , keys nt*8 + 2*t4 ..
-        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);    // row g4+8
+        pa[nt >> 1][(nt & 1) * 2] = pack16(p0, p1);        // row g4   , keys nt*8 + 2*t4 ..
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack16(p2, p3);    // row g4+8
       }
       pa[3][2] = 0u; pa[3][3] = 0u;                            // keys 56..63 do not exist
       sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_
           mma16816(o, pa[kk], bv);
         }
         const int col = h * HD + nt2 * 8 + 2 * t4;
-        if (tok0 >= 0) *reinterpret_cast<uint32_t*>(ctx + (size_t)tok0 * C + col) = pack_bf16(o[0] * inv0, o[1] * inv0);
-        if (tok1 >= 0) *reinterpret_cast<uint32_t*>(ctx + (size_t)tok1 * C + col) = pack_bf16(o[2] * inv1, o[3] * inv1);
+        if (tok0 >= 0) *reinterpret_cast<uint32_t*>(ctx + (size_t)tok0 * C + col) = pack16(o[0] * inv0, o[1] * inv0);
+        if (tok1 >= 0) *reinterpret_cast<uint32_t*>(ctx + (size_t)tok1 * C + col) = pack16(o[2] * inv1, o[3] * inv1);
       }
     }
     __syncwarp();      // all lanes are done with the tiles before the next item overwrites them
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const __nv_
 
 }  // namespace
 
-int window_attention(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
-                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx) {
+int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
+                     int H, int W, int C, int heads, int shift, h16* ctx) {
   HM_CHECK(C == heads * HD, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   HM_CHECK(C % 8 == 0, "window_attention: C must be a multiple of 8");
   const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;

@@ -38,7 +38,7 @@ struct MergeSrc {
 template <class Src>
 __global__ void __launch_bounds__(256) layernorm_kernel(Src src, int rows, int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
-                                                        __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
+                                                        h16* __restrict__ out16, float* __restrict__ out32) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Src src, int rows, int C
       y.z = (v[i].z - mean) * rstd * g.z + b.z;
       y.w = (v[i].w - mean) * rstd * g.w + b.w;
       if (out16 != nullptr)
-        reinterpret_cast<uint2*>(out16 + (size_t)row * C)[idx] = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+        reinterpret_cast<uint2*>(out16 + (size_t)row * C)[idx] = make_uint2(pack16(y.x, y.y), pack16(y.z, y.w));
       if (out32 != nullptr) reinterpret_cast<float4*>(out32 + (size_t)row * C)[idx] = y;
     }
   }
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(Src src, int rows, int C
 template <int C, int V, bool MERGE>
 __global__ void __launch_bounds__(256) layernorm_c_kernel(const float* __restrict__ x, int rows, int H, int W,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
+                                                          h16* __restrict__ out16, float* __restrict__ out32) {
   constexpr int G = C / (4 * V), RPW = 32 / G;
   static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0 && G * 4 * V == C, "bad LayerNorm geometry");
   constexpr bool PARAMS_IN_REGS = V <= 3;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) layernorm_c_kernel(const float* __restric
       y.x = v[i].x * rstd * gg.x + bb.x; y.y = v[i].y * rstd * gg.y + bb.y;
       y.z = v[i].z * rstd * gg.z + bb.z; y.w = v[i].w * rstd * gg.w + bb.w;
       if (out16 != nullptr)
-        reinterpret_cast<uint2*>(out16 + (size_t)row * C)[idx] = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+        reinterpret_cast<uint2*>(out16 + (size_t)row * C)[idx] = make_uint2(pack16(y.x, y.y), pack16(y.z, y.w));
       if (out32 != nullptr) reinterpret_cast<float4*>(out32 + (size_t)row * C)[idx] = y;
     }
   }
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) layernorm_c_kernel(const float* __restric
 
 template <int C, int V, bool MERGE>
 int launch_ln_c(cudaStream_t st, const float* x, int rows, int H, int W, const float* gamma, const float* beta,
-                __nv_bfloat16* out16, float* out32) {
+                h16* out16, float* out32) {
   constexpr int RPW = 32 / (C / (4 * V));
   int blocks = ceil_div(rows, 8 * RPW);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -239,11 +239,11 @@ struct WinSmem {
   int region[WN];
 };
 
-__global__ void __launch_bounds__(HC * 64) window_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(HC * 64) window_attn_kernel(const h16* __restrict__ qkv,
                                                               const float* __restrict__ qkv_bias,
                                                               const float* __restrict__ rel_bias, int H, int W, int C,
                                                               int sh, int sw, int Hp, int Wp,
-                                                              __nv_bfloat16* __restrict__ ctx) {
+                                                              h16* __restrict__ ctx) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   WinSmem& s = *reinterpret_cast<WinSmem*>(smem_raw);
   const int nww = Wp / WS;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(HC * 64) window_attn_kernel(const __nv_bfloat1
   // relative position bias of these 3 heads -> smem (coalesced)
   for (int i = tid; i < HC * WN * WN; i += blockDim.x) (&s.bias[0][0][0])[i] = __ldg(rel_bias + (size_t)h0 * WN * WN + i);
   __syncthreads();
-  // K and V rows of the window: 16-byte chunks of 8 bf16
+  // K and V rows of the window: 16-byte chunks of 8 fp16
   for (int i = tid; i < HC * WN * 4 * 2; i += blockDim.x) {
     const int chunk = i & 3, kv = (i >> 2) & 1, p = (i >> 3) % WN, h = (i >> 3) / WN;
     const int col = (1 + kv) * C + (h0 + h) * HD + chunk * 8;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(HC * 64) window_attn_kernel(const __nv_bfloat1
     const int tok = s.tok[p];
     if (tok >= 0) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + col));
-      float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      float2 a = unpack16(u.x), bb = unpack16(u.y), cc = unpack16(u.z), d = unpack16(u.w);
       dst[0] = a.x; dst[1] = a.y; dst[2] = bb.x; dst[3] = bb.y; dst[4] = cc.x; dst[5] = cc.y; dst[6] = d.x; dst[7] = d.y;
     } else {
 #pragma unroll
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(HC * 64) window_attn_kernel(const __nv_bfloat1
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
       const uint4 u = __ldg(qp + c4);
-      float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      float2 a = unpack16(u.x), bb = unpack16(u.y), cc = unpack16(u.z), d = unpack16(u.w);
       q[8 * c4 + 0] = a.x * scale; q[8 * c4 + 1] = a.y * scale; q[8 * c4 + 2] = bb.x * scale; q[8 * c4 + 3] = bb.y * scale;
       q[8 * c4 + 4] = cc.x * scale; q[8 * c4 + 5] = cc.y * scale; q[8 * c4 + 6] = d.x * scale; q[8 * c4 + 7] = d.y * scale;
     }
@@ -339,14 +339,14 @@ __global__ void __launch_bounds__(HC * 64) window_attn_kernel(const __nv_bfloat1
   uint4* op = reinterpret_cast<uint4*>(ctx + (size_t)tok * C + (h0 + h) * HD);
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4)
-    op[c4] = make_uint4(pack_bf16(acc[8 * c4] * inv, acc[8 * c4 + 1] * inv), pack_bf16(acc[8 * c4 + 2] * inv, acc[8 * c4 + 3] * inv),
-                        pack_bf16(acc[8 * c4 + 4] * inv, acc[8 * c4 + 5] * inv), pack_bf16(acc[8 * c4 + 6] * inv, acc[8 * c4 + 7] * inv));
+    op[c4] = make_uint4(pack16(acc[8 * c4] * inv, acc[8 * c4 + 1] * inv), pack16(acc[8 * c4 + 2] * inv, acc[8 * c4 + 3] * inv),
+                        pack16(acc[8 * c4 + 4] * inv, acc[8 * c4 + 5] * inv), pack16(acc[8 * c4 + 6] * inv, acc[8 * c4 + 7] * inv));
 }
 
 }  // namespace
 
 int layernorm(cudaStream_t st, const float* x, int rows, int C, const float* gamma, const float* beta,
-              __nv_bfloat16* out16, float* out32) {
+              h16* out16, float* out32) {
   HM_CHECK(C % 4 == 0 && C <= LN_MAXV * 128, "layernorm: C=%d unsupported (multiple of 4, <= %d)", C, LN_MAXV * 128);
   HM_CHECK(rows > 0, "layernorm: empty input");
   switch (C) {      // the Swin-T widths get the lane-exact kernel
@@ -363,7 +363,7 @@ int layernorm(cudaStream_t st, const float* x, int rows, int C, const float* gam
 }
 
 int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin, const float* gamma,
-                   const float* beta, __nv_bfloat16* out16) {
+                   const float* beta, h16* out16) {
   HM_CHECK(H % 2 == 0 && W % 2 == 0, "patch_merge: odd grid %dx%d (the reference pads; never hit at 96x320)", H, W);
   HM_CHECK(Cin % 4 == 0 && 4 * Cin <= LN_MAXV * 128, "patch_merge: C=%d unsupported", Cin);
   const int rows = B * (H / 2) * (W / 2);
@@ -390,8 +390,8 @@ int patch_embed(cudaStream_t st, const float* images, int B, const float* w, con
 }
 
 // CUDA-core fp32 version (round-1 first path); kept as an independent implementation for A/B tests.
-int window_attention_fp32(cudaStream_t st, const __nv_bfloat16* qkv, const float* qkv_bias, const float* rel_bias, int B,
-                     int H, int W, int C, int heads, int shift, __nv_bfloat16* ctx) {
+int window_attention_fp32(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
+                     int H, int W, int C, int heads, int shift, h16* ctx) {
   HM_CHECK(C == heads * HD, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   HM_CHECK(heads % HC == 0, "window_attention: heads=%d must be a multiple of %d", heads, HC);
   const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;

@@ -114,15 +114,15 @@ int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_ms);
 /* ---- individual kernels, exported for the unit tests ------------------------------------- */
 
 /* nn.Linear (+ fused epilogue): out = LN?( act(A W^T + bias) + residual )
- * A bf16 [M,K] pitch lda, W bf16 [N,K]; act 0 none / 1 GELU(erf) / 2 ReLU; any of bias, residual,
- * out_f32, out_bf16, ln_gamma/ln_beta may be NULL.  force_bn 0 = automatic tile width. */
-int hmocr_gemm_bf16(const void* a_dev, int lda, int M, int K, const void* w_dev, int N, const float* bias_dev,
-                    int act, const float* residual_dev, int ldr, float* out_f32_dev, int ld32, void* out_bf16_dev,
+ * A fp16 [M,K] pitch lda, W fp16 [N,K]; act 0 none / 1 GELU(erf) / 2 ReLU; any of bias, residual,
+ * out_f32, out_f16, ln_gamma/ln_beta may be NULL.  force_bn 0 = automatic tile width. */
+int hmocr_gemm_f16(const void* a_dev, int lda, int M, int K, const void* w_dev, int N, const float* bias_dev,
+                    int act, const float* residual_dev, int ldr, float* out_f32_dev, int ld32, void* out_f16_dev,
                     int ld16, const float* ln_gamma_dev, const float* ln_beta_dev, int force_bn, void* stream);
 
-/* nn.LayerNorm over the last axis: x f32 [rows, C] -> bf16 and/or f32 */
+/* nn.LayerNorm over the last axis: x f32 [rows, C] -> fp16 and/or f32 */
 int hmocr_layernorm(const float* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
-                    void* out_bf16_dev, float* out_f32_dev, void* stream);
+                    void* out_f16_dev, float* out_f32_dev, void* stream);
 
 /* features[0]: Conv2d(1,96,4,4) + Permute + LayerNorm(96)   (swin_transformer.py:556-562)
  * images f32 [B,1,96,320] -> x f32 [B,24,80,96] */
@@ -130,17 +130,17 @@ int hmocr_patch_embed(const float* images_dev, int batch, const float* conv_w_de
                       const float* ln_g_dev, const float* ln_b_dev, float* x_dev, void* stream);
 
 /* PatchMerging gather + LayerNorm(4C)            (swin_transformer.py:35-43, 84)
- * x f32 [B,H,W,C] -> bf16 [B,H/2,W/2,4C] (ready for the bias-free reduction GEMM) */
+ * x f32 [B,H,W,C] -> fp16 [B,H/2,W/2,4C] (ready for the bias-free reduction GEMM) */
 int hmocr_patch_merge_ln(const float* x_dev, int batch, int H, int W, int C, const float* gamma_dev,
-                         const float* beta_dev, void* out_bf16_dev, void* stream);
+                         const float* beta_dev, void* out_f16_dev, void* stream);
 
 /* shifted_window_attention core (swin_transformer.py:151-214, 219-227) on a qkv buffer computed
  * for the real (un-padded, un-shifted) tokens:
- *   qkv bf16 [B*H*W, 3C] (bias included), qkv_bias f32 [3C] (value of padded tokens),
+ *   qkv fp16 [B*H*W, 3C] (bias included), qkv_bias f32 [3C] (value of padded tokens),
  *   rel_bias f32 [heads,49,49] (table gathered by relative_position_index), shift 0 or 3
- *   -> ctx bf16 [B*H*W, C] in original token order (input of attn.proj) */
+ *   -> ctx fp16 [B*H*W, C] in original token order (input of attn.proj) */
 int hmocr_window_attention(const void* qkv_dev, const float* qkv_bias_dev, const float* rel_bias_dev, int batch,
-                           int H, int W, int C, int heads, int shift, void* ctx_bf16_dev, void* stream);
+                           int H, int W, int C, int heads, int shift, void* ctx_f16_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,16 +14,16 @@ def S():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def gemm(a16, w16, bias=None, act=0, residual=None, out_f32=True, out_bf16=False, ln=None, force_bn=0, lda=None):
+def gemm(a16, w16, bias=None, act=0, residual=None, out_f32=True, out_f16=False, ln=None, force_bn=0, lda=None):
     lib = _lib.load()
     M, K = a16.shape
     N = w16.shape[0]
     o32 = torch.empty(M, N, dtype=torch.float32, device="cuda") if out_f32 else None
-    o16 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda") if out_bf16 else None
+    o16 = torch.empty(M, N, dtype=torch.float16, device="cuda") if out_f16 else None
     g, b = (ln if ln is not None else (None, None))
-    rc = lib.hmocr_gemm_bf16(P(a16), lda or a16.stride(0), M, K, P(w16), N, P(bias), act, P(residual),
+    rc = lib.hmocr_gemm_f16(P(a16), lda or a16.stride(0), M, K, P(w16), N, P(bias), act, P(residual),
                              N if residual is not None else 0, P(o32), N, P(o16), N, P(g), P(b), force_bn, S())
-    _lib.check(rc, "hmocr_gemm_bf16")
+    _lib.check(rc, "hmocr_gemm_f16")
     torch.cuda.synchronize()
     return o32, o16
 

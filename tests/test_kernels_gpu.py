@@ -34,9 +34,9 @@ GEMM_SHAPES = [
 
 @pytest.mark.parametrize("M,K,N", GEMM_SHAPES)
 def test_gemm_plain(M, K, N):
-    a = _rand(M, K, seed=1).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
-    o32, o16 = gemm(a, w, out_bf16=True)
+    a = _rand(M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    o32, o16 = gemm(a, w, out_f16=True)
     ref = gemm_ref(a, w)
     err = (o32 - ref).abs().max().item()
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err      # fp32 accumulation-order noise only
@@ -46,8 +46,8 @@ def test_gemm_plain(M, K, N):
 @pytest.mark.parametrize("bn", [64, 96, 128, 192, 256])
 def test_gemm_every_tile_width(bn):
     M, K, N = 1000, 320, bn * 3
-    a = _rand(M, K, seed=3).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=4).bfloat16()
+    a = _rand(M, K, seed=3).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=4).half()
     o32, _ = gemm(a, w, force_bn=bn)
     assert (o32 - gemm_ref(a, w)).abs().max().item() < 3e-3
 
@@ -55,10 +55,10 @@ def test_gemm_every_tile_width(bn):
 @pytest.mark.parametrize("act", [0, 1, 2])
 def test_gemm_bias_act_residual(act):
     M, K, N = 777, 384, 192
-    a = _rand(M, K, seed=5).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=6).bfloat16()
+    a = _rand(M, K, seed=5).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=6).half()
     bias, res = _rand(N, seed=7), _rand(M, N, seed=8)
-    o32, o16 = gemm(a, w, bias=bias, act=act, residual=res, out_bf16=True)
+    o32, o16 = gemm(a, w, bias=bias, act=act, residual=res, out_f16=True)
     ref = gemm_ref(a, w, bias, act, res)
     assert (o32 - ref).abs().max().item() < 3e-3
     assert (o16.float() - ref).abs().max().item() < 5e-2
@@ -67,12 +67,12 @@ def test_gemm_bias_act_residual(act):
 def test_gemm_residual_in_place():
     lib, L = _lib()
     M, K, N = 500, 96, 96
-    a = _rand(M, K, seed=9).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=10).bfloat16()
+    a = _rand(M, K, seed=9).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=10).half()
     bias = _rand(N, seed=11)
     x = _rand(M, N, seed=12)
     ref = gemm_ref(a, w, bias, 0, x.clone())
-    L.check(lib.hmocr_gemm_bf16(P(a), K, M, K, P(w), N, P(bias), 0, P(x), N, P(x), N, None, 0, None, None, 0, S()), "gemm")
+    L.check(lib.hmocr_gemm_f16(P(a), K, M, K, P(w), N, P(bias), 0, P(x), N, P(x), N, None, 0, None, None, 0, S()), "gemm")
     torch.cuda.synchronize()
     assert (x - ref).abs().max().item() < 3e-3
 
@@ -80,11 +80,11 @@ def test_gemm_residual_in_place():
 @pytest.mark.parametrize("N,K", [(256, 256), (256, 512), (96, 96), (192, 768)])
 def test_gemm_fused_layernorm(N, K):
     M = 300
-    a = _rand(M, K, seed=13).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=14).bfloat16()
+    a = _rand(M, K, seed=13).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=14).half()
     bias, res = _rand(N, seed=15), _rand(M, N, seed=16)
     g, b = 1 + 0.2 * _rand(N, seed=17), 0.1 * _rand(N, seed=18)
-    o32, o16 = gemm(a, w, bias=bias, residual=res, ln=(g, b), out_bf16=True)
+    o32, o16 = gemm(a, w, bias=bias, residual=res, ln=(g, b), out_f16=True)
     ref = gemm_ref(a, w, bias, 0, res, (g, b))
     assert (o32 - ref).abs().max().item() < 3e-3
     assert (o16.float() - ref).abs().max().item() < 5e-2
@@ -92,10 +92,10 @@ def test_gemm_fused_layernorm(N, K):
 
 def test_gemm_rejects_bad_shapes():
     lib, L = _lib()
-    a = _rand(8, 64).bfloat16()
-    w = _rand(40, 64).bfloat16()
+    a = _rand(8, 64).half()
+    w = _rand(40, 64).half()
     out = torch.empty(8, 40, device="cuda")
-    rc = lib.hmocr_gemm_bf16(P(a), 64, 8, 64, P(w), 40, None, 0, None, 0, P(out), 40, None, 0, None, None, 0, S())
+    rc = lib.hmocr_gemm_f16(P(a), 64, 8, 64, P(w), 40, None, 0, None, 0, P(out), 40, None, 0, None, None, 0, S())
     assert rc != 0 and b"multiple of 32" in lib.hmocr_last_error()
 
 
@@ -105,7 +105,7 @@ def test_layernorm(C_):
     rows = 1000
     x = _rand(rows, C_, seed=20) * 3 + 0.5
     g, b = 1 + 0.2 * _rand(C_, seed=21), 0.1 * _rand(C_, seed=22)
-    o16 = torch.empty(rows, C_, dtype=torch.bfloat16, device="cuda")
+    o16 = torch.empty(rows, C_, dtype=torch.float16, device="cuda")
     o32 = torch.empty(rows, C_, dtype=torch.float32, device="cuda")
     L.check(lib.hmocr_layernorm(P(x), rows, C_, P(g), P(b), P(o16), P(o32), S()), "layernorm")
     torch.cuda.synchronize()
@@ -135,7 +135,7 @@ def test_patch_merge_ln(H, W, Cin):
     B = 2
     x = _rand(B, H, W, Cin, seed=30)
     g, b = 1 + 0.2 * _rand(4 * Cin, seed=31), 0.1 * _rand(4 * Cin, seed=32)
-    out = torch.empty(B, H // 2, W // 2, 4 * Cin, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(B, H // 2, W // 2, 4 * Cin, dtype=torch.float16, device="cuda")
     L.check(lib.hmocr_patch_merge_ln(P(x), B, H, W, Cin, P(g), P(b), P(out), S()), "patch_merge_ln")
     torch.cuda.synchronize()
     cat = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
@@ -163,10 +163,10 @@ def test_window_attention_against_oracle(stage, shift):
     from oracle.synth import relative_position_index
     idx = torch.from_numpy(relative_position_index()).cuda()
     dsd[bp + "attn.relative_position_index"] = idx
-    # feed both sides the SAME bf16-rounded qkv so only the attention core is compared
-    qkv = torch.nn.functional.linear(xn, dsd[bp + "attn.qkv.weight"], dsd[bp + "attn.qkv.bias"]).bfloat16()
+    # feed both sides the SAME fp16-rounded qkv so only the attention core is compared
+    qkv = torch.nn.functional.linear(xn, dsd[bp + "attn.qkv.weight"], dsd[bp + "attn.qkv.bias"]).half()
     rel = dsd[bp + "attn.relative_position_bias_table"][idx].reshape(49, 49, heads).permute(2, 0, 1).contiguous()
-    ctx = torch.zeros(B * H * W, C_, dtype=torch.bfloat16, device="cuda")
+    ctx = torch.zeros(B * H * W, C_, dtype=torch.float16, device="cuda")
     L.check(lib.hmocr_window_attention(P(qkv), P(dsd[bp + "attn.qkv.bias"]), P(rel), B, H, W, C_, heads, shift, P(ctx), S()),
             "window_attention")
     torch.cuda.synchronize()

@@ -1,12 +1,13 @@
 """GPU parity of the engine (through the C ABI) against the golden vectors of the real reference
 and against the oracle run on the same seeded inputs.
 
-Stated tolerances (north_star: "within a stated bf16/fp32 tolerance"):
-  * encoder features: bf16 tensor-core GEMMs + bf16 activations between kernels, fp32 residual
-    stream / LayerNorm / softmax  ->  max-abs error <= 6e-2 on features with std ~1.2 (|max| ~4)
-  * teacher-forced logits (std ~4): max-abs error <= 1.5e-1
+Stated tolerances (north_star: "within a stated bf16/fp32 tolerance ... e.g. max-abs logit error <= 1e-2"):
+  * the engine computes in fp16 operands (saturating conversions), fp32 accumulation, fp32 residual stream /
+    LayerNorm / softmax
+  * encoder features (std ~1.2, |max| ~4): max-abs error <= 1e-2            (measured 3.7e-3)
+  * teacher-forced logits (std ~4):        max-abs error <= 1e-2            (measured 7.8e-3)
   * greedy tokens: identical, or first divergence at a step whose reference top1-top2 margin is
-    below 2x the measured max logit error (a near-tie, allowed by north_star).
+    below 2x the logit tolerance (a near-tie, allowed by north_star; measured margins <= 3.2e-3).
 """
 import numpy as np
 import pytest
@@ -14,12 +15,12 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-FEAT_TOL = 6e-2
-LOGIT_TOL = 1.5e-1
-# the persistent decode kernel on identical encoder features (fp16 operands, fp32 accumulate / residual /
-# LayerNorm / softmax): measured max |log p(winner) - oracle| 1.3e-2, largest oracle margin at a divergence 1.8e-2
-DECODE_LOGP_TOL = 5e-2
-DECODE_TIE_MARGIN = 6e-2
+FEAT_TOL = 1e-2
+LOGIT_TOL = 1e-2
+# the persistent decode kernel on identical encoder features: measured max |log p(winner) - oracle| 5.0e-3,
+# largest oracle margin at a divergence 2.4e-3 (58/64 sequences of 60 steps identical)
+DECODE_LOGP_TOL = 1.5e-2
+DECODE_TIE_MARGIN = 1e-2
 
 
 @pytest.fixture(scope="module")
@@ -147,9 +148,9 @@ def test_incremental_decode_matches_teacher_forced(model, golden_src):
     logits = model.decoder(feats, tokens[:, :-1])
     lsm = torch.log_softmax(logits, -1)
     chosen = lsm.gather(-1, tokens[:, 1:].unsqueeze(-1)).squeeze(-1)
-    assert (chosen - logp).abs().max().item() < 5e-2
+    assert (chosen - logp).abs().max().item() < 1.5e-2
     near = (lsm.max(-1).values - chosen)       # 0 where the cached path picked the teacher-forced argmax
-    assert (near < 5e-2).all()
+    assert (near < 1.5e-2).all()
 
 
 def test_persistent_kernel_agrees_with_step_graph(model, golden_src):
@@ -170,7 +171,7 @@ def test_persistent_kernel_agrees_with_step_graph(model, golden_src):
             n = c - 1
         else:
             n = a_steps
-        assert (a_lp[r, :n] - b_lp[r, :n]).abs().max().item() < 5e-2
+        assert (a_lp[r, :n] - b_lp[r, :n]).abs().max().item() < 1.5e-2
 
 
 @pytest.mark.parametrize("steps_per_launch", [1, 7, 64])
@@ -300,4 +301,4 @@ def test_greedy_agreement_on_a_larger_sample(model, sd, cfg):
           f"max |log p(winner) - oracle| on agreeing prefixes: {err:.4f}; oracle margins at the divergences: "
           f"max {max(div_margins) if div_margins else 0:.4f}, median {float(np.median(div_margins)) if div_margins else 0:.4f}")
     assert err < DECODE_LOGP_TOL
-    assert same >= 40
+    assert same >= 48
