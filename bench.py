@@ -280,7 +280,7 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "tokens_per_sec": total_imgs * T / (ms_step * 1e-3),
             "p50_ms_per_image_b1": statistics.median(lat), "ms_per_image_at_batch": ms_step / B,
             "encoder_ms": ms_enc, "decode_ms": ms_dec, "wall_ms_per_step": wall * 1e3 / args.steps,
