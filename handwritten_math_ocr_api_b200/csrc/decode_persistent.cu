@@ -53,6 +53,10 @@ constexpr float ATT_SCALE = 0.17677669529663687f * 1.4426950408889634f;   // log
 constexpr float LN_EPS = 1e-5f;
 
 struct __align__(16) Partial { float m; int idx; float s; int pad; };
+// beam search: K best (logit, token) of a row, best first; 48 bytes = three 16-byte DSMEM stores
+struct __align__(16) TopList { float v[DP_MAX_BEAM]; int i[DP_MAX_BEAM]; int pad[2]; };
+struct Cand { float score; int flat; };
+struct Sel { float score; int parent; int tok; };
 
 struct Smem {
   alignas(128) uint8_t slot[NW][DP_CHUNK];  // warp-private weight slots
@@ -68,11 +72,19 @@ struct Smem {
   alignas(16) __half vnew[R][HD];
   Partial part[CL][R];                      // per-CTA argmax / sum-exp partials (gathered)
   Partial wpart[NW][R];                     // per-warp partials
+  // beam search only
+  TopList wtop[NW][R];                      // per-warp top-K logits of every row
+  TopList ctop[CL][R];                      // per-CTA top-K, gathered from the 8 CTAs
+  Cand cand[R][DP_MAX_BEAM];                // candidate (score, hypothesis * V + token) of every row
+  Sel sel[R];                               // chosen (score, parent row, token) of every new hypothesis
+  float bscore[R];
+  int bfin[R], bsrc[R];
   alignas(8) uint64_t full[NW];
-  alignas(8) uint64_t xbar[4];              // exchange barriers: context, y, hidden, partials
+  alignas(8) uint64_t xbar[5];              // exchange barriers: context, y, hidden, partials, top-K lists
 };
-enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3 };
+enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3, X_TOP = 4 };
 constexpr uint32_t XB_CTX = R * D * 2, XB_Y = R * D * 4, XB_HF = R * FF * 2, XB_PART = CL * R * sizeof(Partial);
+constexpr uint32_t XB_TOP = CL * R * sizeof(TopList);
 static_assert(sizeof(Smem) <= 112 * 1024, "two CTAs must fit one SM");
 static_assert(sizeof(float) * 4 * 16 * 9 >= sizeof(__half) * R * 72, "hidden staging aliases stg");
 
@@ -231,10 +243,17 @@ __device__ __forceinline__ void attend_issue(const __half* Kc, int n, int lane, 
   for (int b = 0; b < 4 && b < NB; ++b)
     if (b < nb) load_block(Kl, b, kv.r[b]);
 }
-template <int NB, bool NEW>
+// If COPY (beam search), every consumed history block is also stored to (Kd, Vd): the destination row of the
+// other cache set - the parent gather of the beam reorder rides on the attention loads.
+__device__ __forceinline__ void store_block(uint4* base, int b, const uint4 (&d)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) __stcg(base + 128 * b + 32 * u, d[u]);
+}
+template <int NB, bool NEW, bool COPY>
 __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, const __half* Vc, int n,
                                            const __half* knew, const __half* vnew, uint32_t* pbuf, int lane,
-                                           KvSlots& kv, float (&out)[4], long long* tr) {
+                                           KvSlots& kv, float (&out)[4], long long* tr, __half* Kd = nullptr,
+                                           __half* Vd = nullptr) {
   const int g4 = lane >> 2, t4 = lane & 3;
   const uint2 q0 = *reinterpret_cast<const uint2*>(qh + 4 * t4), q1 = *reinterpret_cast<const uint2*>(qh + 16 + 4 * t4);
   const int nb = (n + 31) >> 5;
@@ -269,6 +288,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
         sc[4 * b + 2 * tile] = (key < n) ? c[0] : -INFINITY;
         sc[4 * b + 2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
       }
+      if (COPY) store_block(reinterpret_cast<uint4*>(Kd) + lane, b, d);
       if (b + 4 < NB && b + 4 < nb) load_block(Kl, b + 4, d);       // next K block of this slot ...
       else load_block(Vl, b & 3, d);                                // ... or its first V block (b & 3 < nb here)
     } else {
@@ -309,6 +329,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
       mma_f16(acc1, d[1].x, d[1].y, d[1].z, d[1].w, p0.x, p0.y);
       mma_f16(acc0, d[2].x, d[2].y, d[2].z, d[2].w, p1.x, p1.y);
       mma_f16(acc1, d[3].x, d[3].y, d[3].z, d[3].w, p1.x, p1.y);
+      if (COPY) store_block(reinterpret_cast<uint4*>(Vd) + lane, b, d);
       if (b + 4 < NB && b + 4 < nb) load_block(Vl, b + 4, d);
     }
   }
@@ -354,21 +375,68 @@ __device__ __forceinline__ Partial shfl_partial(const Partial& a, int o) {
 
 struct LnRegs { float4 g0, g1, b0, b1; };
 
+// ---- beam search: per-thread / per-warp top-K lists ------------------------------------------------------
+// order of candidates: higher value first; equal values: lower index first (torch's stable descending sort)
+__device__ __forceinline__ bool cand_before(float v, int i, float w, int j) { return v > w || (v == w && i < j); }
+template <int KB>
+struct TopK {
+  float v[KB];
+  int i[KB];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+  }
+  __device__ __forceinline__ void insert(float x, int idx) {
+    if (!cand_before(x, idx, v[KB - 1], i[KB - 1])) return;
+    v[KB - 1] = x; i[KB - 1] = idx;
+#pragma unroll
+    for (int k = KB - 1; k > 0; --k) {
+      const bool sw = cand_before(v[k], i[k], v[k - 1], i[k - 1]);
+      const float tv = v[k]; const int ti = i[k];
+      v[k] = sw ? v[k - 1] : v[k]; i[k] = sw ? i[k - 1] : i[k];
+      v[k - 1] = sw ? tv : v[k - 1]; i[k - 1] = sw ? ti : i[k - 1];
+    }
+  }
+  __device__ __forceinline__ void merge_xor(int mask) {           // butterfly step: both lanes end with the union's top-K
+    float ov[KB]; int oi[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { ov[k] = __shfl_xor_sync(0xffffffffu, v[k], mask); oi[k] = __shfl_xor_sync(0xffffffffu, i[k], mask); }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) insert(ov[k], oi[k]);
+  }
+  __device__ __forceinline__ void store(TopList& d) const {
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { d.v[k] = v[k]; d.i[k] = i[k]; }
+  }
+  __device__ __forceinline__ void load(const TopList& d) {
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { v[k] = d.v[k]; i[k] = d.i[k]; }
+  }
+};
+template <>
+struct TopK<0> {                                                  // greedy instantiation: no state, no work
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void insert(float, int) {}
+};
+
 // The fp32 bias of weight row r travels in the padding of that row (halves 256, 257 of 264): it arrives with
 // the weights, costs no extra copy, barrier or shared memory, and is read before the slot is released.
 __device__ __forceinline__ float chunk_bias(const uint8_t* slot, int r) {
   return *reinterpret_cast<const float*>(slot + (r * PD + D) * 2);
 }
 
-template <int NB>
+// KB = 0: greedy.  KB = DP_MAX_BEAM: beam search with p.beam <= KB hypotheses per image (see decode_persistent.cuh).
+template <int NB, int KB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
+  constexpr bool BEAM = KB > 0;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = (int)cluster_ctarank();              // feature slice == attention head
-  const int row0 = (blockIdx.x / CL) * R;
-  const int nrows = min(R, p.rows - row0);           // valid rows of this cluster (1..8)
+  const int RPC = BEAM ? p.rows_per_cluster : R;     // rows owned by one cluster
+  const int row0 = (blockIdx.x / CL) * RPC;
+  const int nrows = min(RPC, p.rows - row0);         // valid rows of this cluster (1..8)
   const int g4 = lane >> 2, t4 = lane & 3;           // mma fragment coordinates
   const int L = p.num_layers, S = p.chunks_per_step, FT = p.fc_tiles;
   const int total_chunks = (t_end - t_begin) * S;
@@ -405,7 +473,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     if (lane == 0 && !dbg_noweights) slot_fetch();
   };
   // ---- exchanges --------------------------------------------------------------------------------------
-  uint32_t ph_ctx = 0, ph_y = 0, ph_hf = 0, ph_part = 0;
+  uint32_t ph_ctx = 0, ph_y = 0, ph_hf = 0, ph_part = 0, ph_top = 0;
   auto xwait = [&](int X, uint32_t& ph, uint32_t bytes) {
     mbar_wait_cluster(&s.xbar[X], ph & 1);
     ++ph;
@@ -503,15 +571,27 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
 
   if (tid == 0) {
     for (int i = 0; i < NW; ++i) mbar_init(&s.full[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&s.xbar[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&s.xbar[i], 1);
     fence_barrier_init();
     mbar_expect_tx(&s.xbar[X_CTX], XB_CTX);
     mbar_expect_tx(&s.xbar[X_Y], XB_Y);
     mbar_expect_tx(&s.xbar[X_HF], XB_HF);
     mbar_expect_tx(&s.xbar[X_PART], XB_PART);
+    mbar_expect_tx(&s.xbar[X_TOP], XB_TOP);
   }
-  embed_row(t_begin, p.tokens[(size_t)my_row * p.ld_tok + t_begin]);
+  if (BEAM && tid < R) {                              // hypothesis state of this cluster's rows (kept in HBM between launches)
+    const bool ok = tid < nrows;
+    s.bscore[tid] = ok ? p.bm_score[row0 + tid] : -INFINITY;
+    s.bfin[tid] = ok ? p.bm_fin[row0 + tid] : 1;
+    s.bsrc[tid] = ok ? p.bm_src[row0 + tid] : nrows - 1;
+  }
+  embed_row(t_begin, BEAM ? (long long)p.bm_tok[my_row] : p.tokens[(size_t)my_row * p.ld_tok + t_begin]);
   __syncthreads();
+  bool cluster_done = false;                          // beam search: every hypothesis of this cluster has emitted eos
+  if (BEAM && tid == 0) {
+    cluster_done = true;
+    for (int r = 0; r < nrows; ++r) cluster_done = cluster_done && s.bfin[r] != 0;
+  }
   cluster_sync_all();      // every CTA of the cluster is resident and its barriers are armed before any DSMEM store
   if (lane == 0) slot_fetch();
 
@@ -527,9 +607,16 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     // where this step's key / value go inside the (layer, row, head) region of the fragment-major caches
     const int k_app = (t >> 5) * 512 + kfrag_word(t & 31, lane & 15);       // 32-bit word index (lanes 0..15)
     const int v_app = (t >> 5) * 1024 + vfrag_half(t & 31, lane);           // half index (lane = dim)
+    // beam search: history is read from the parent's row of set (t & 1) and re-written, with this step's
+    // key/value, to this hypothesis' own row of the other set; greedy: one set, one row
+    const size_t set_rd = BEAM ? (size_t)(t & 1) * p.cache_set_stride : 0;
+    const size_t set_wr = BEAM ? (size_t)((t & 1) ^ 1) * p.cache_set_stride : 0;
+    const size_t kv_src = BEAM ? ((size_t)(row0 + s.bsrc[min(warp, nrows - 1)]) * NH + c) * kv_rh : kv_row;
     for (int l = 0; l < L; ++l) {
-      __half* Kc = p.kcache + (size_t)l * kv_layer + kv_row;            // caches of (row `warp`, head c)
-      __half* Vc = p.vcache + (size_t)l * kv_layer + kv_row;
+      const __half* Kc = p.kcache + set_rd + (size_t)l * kv_layer + kv_src;     // history of (row `warp`, head c)
+      const __half* Vc = p.vcache + set_rd + (size_t)l * kv_layer + kv_src;
+      __half* Kd = p.kcache + set_wr + (size_t)l * kv_layer + kv_row;           // where this step's key / value go
+      __half* Vd = p.vcache + set_wr + (size_t)l * kv_layer + kv_row;
       const __half* Mk = p.memk + (size_t)l * m_layer + m_row;
       const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
       TR();
@@ -566,19 +653,22 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       {
         float o[4];
         long long* tr = (tracing && t == p.trace_step && ti + 3 < 1024) ? p.trace + ti : nullptr;
-        attend_mma<NB, true>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0], lane,
-                             kv, o, tr);
+        attend_mma<NB, true, BEAM>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0],
+                                   lane, kv, o, tr, Kd, Vd);
         if (tr) ti += 3;
         send_ctx(o);
+        if (BEAM) __syncwarp();                                // the block copies above are ordered before the append
         if (row_ok) {                                          // append this step's key / value (fragment-major)
-          if (lane < 16) reinterpret_cast<uint32_t*>(Kc)[k_app] = reinterpret_cast<const uint32_t*>(&s.knew[warp][0])[lane];
-          Vc[v_app] = s.vnew[warp][lane];
+          if (lane < 16) reinterpret_cast<uint32_t*>(Kd)[k_app] = reinterpret_cast<const uint32_t*>(&s.knew[warp][0])[lane];
+          Vd[v_app] = s.vnew[warp][lane];
         }
         // self-attention cache of the NEXT layer (next step's layer 0 after the last one) -> L2
-        const int ln = (l + 1 < L) ? l + 1 : 0;
-        const int keys = (l + 1 < L) ? t : t + 1;
-        if (keys > 0 && lane < 2 && !(p.flags & 1))
-          prefetch_l2((lane ? p.vcache : p.kcache) + (size_t)ln * kv_layer + kv_row, ((keys + 31) >> 5) * 2048);
+        const bool last = l + 1 == L;
+        const int keys = last ? t + 1 : t;
+        if (keys > 0 && lane < 2 && !(p.flags & 1)) {
+          const size_t nxt = last ? set_wr + kv_row : set_rd + (size_t)(l + 1) * kv_layer + kv_src;
+          prefetch_l2((lane ? p.vcache : p.kcache) + nxt, ((keys + 31) >> 5) * 2048);
+        }
       }
       TR();
       // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
@@ -625,7 +715,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       TR();
       {
         float o[4];
-        attend_mma<1, false>(&s.qh[warp][0], Mk, Mv, MEM_S, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
+        attend_mma<1, false, false>(&s.qh[warp][0], Mk, Mv, MEM_S, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
         send_ctx(o);
       }
       TR();
@@ -702,6 +792,8 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     TR();
     Partial pa, pb;        // rows 2*t4 and 2*t4+1 over this thread's features
     pa.m = pb.m = -INFINITY; pa.idx = pb.idx = 0x7fffffff; pa.s = pb.s = 0.f; pa.pad = pb.pad = 0;
+    TopK<KB> ta, tb;       // beam search: the K best logits of rows 2*t4 / 2*t4+1 seen by this thread
+    ta.init(); tb.init();
     {
       const int j0 = (warp - g) & 7;
 #pragma unroll 1
@@ -712,8 +804,14 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
         slot_release();
         const int lf = m * 16 + g4, v0 = c * cols_per_cta + lf;
-        if (v0 < p.vocab) { update_partial(pa, acc[0] + b0, v0); update_partial(pb, acc[1] + b0, v0); }
-        if (v0 + 8 < p.vocab) { update_partial(pa, acc[2] + b1, v0 + 8); update_partial(pb, acc[3] + b1, v0 + 8); }
+        if (v0 < p.vocab) {
+          update_partial(pa, acc[0] + b0, v0); update_partial(pb, acc[1] + b0, v0);
+          ta.insert(acc[0] + b0, v0); tb.insert(acc[1] + b0, v0);
+        }
+        if (v0 + 8 < p.vocab) {
+          update_partial(pa, acc[2] + b1, v0 + 8); update_partial(pb, acc[3] + b1, v0 + 8);
+          ta.insert(acc[2] + b1, v0 + 8); tb.insert(acc[3] + b1, v0 + 8);
+        }
       }
       g += FT;
     }
@@ -724,6 +822,11 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       merge_partial(pb, ob);
     }
     if (g4 == 0) { s.wpart[warp][2 * t4] = pa; s.wpart[warp][2 * t4 + 1] = pb; }
+    if constexpr (BEAM) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) { ta.merge_xor(o); tb.merge_xor(o); }
+      if (g4 == 0) { ta.store(s.wtop[warp][2 * t4]); tb.store(s.wtop[warp][2 * t4 + 1]); }
+    }
     __syncthreads();
     TR();
     if (warp == 0) {                         // lane = (row, quarter): merge the 8 warps, then send to CTAs 2q, 2q+1
@@ -742,18 +845,36 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         st_async_v4(base + off, v, base + boff);
       }
     }
+    if constexpr (BEAM) {                    // row `warp`: the CTA's K best logits -> every CTA (lane k serves CTA k)
+      TopK<KB> tl;
+      if (lane < NW) tl.load(s.wtop[lane][warp]); else tl.init();
+#pragma unroll
+      for (int o = 1; o < NW; o <<= 1) tl.merge_xor(o);
+      if (lane < CL) {
+        static_assert(KB == 5, "TopList packing below assumes 5 entries");
+        const uint4 v0 = make_uint4(__float_as_uint(tl.v[0]), __float_as_uint(tl.v[1]), __float_as_uint(tl.v[2]), __float_as_uint(tl.v[3]));
+        const uint4 v1 = make_uint4(__float_as_uint(tl.v[4]), (uint32_t)tl.i[0], (uint32_t)tl.i[1], (uint32_t)tl.i[2]);
+        const uint4 v2 = make_uint4((uint32_t)tl.i[3], (uint32_t)tl.i[4], 0u, 0u);
+        const uint32_t base = cl0 + lane * cl_stride;
+        const uint32_t off = base + (smem_u32(&s.ctop[c][warp]) - s_local), bar = base + (smem_u32(&s.xbar[X_TOP]) - s_local);
+        st_async_v4(off, v0, bar);
+        st_async_v4(off + 16, v1, bar);
+        st_async_v4(off + 32, v2, bar);
+      }
+    }
     xwait(X_PART, ph_part, XB_PART);
     TR();
-    {
-      Partial a;
-      if (lane < CL) a = s.part[lane][warp];
-      else { a.m = -INFINITY; a.idx = 0x7fffffff; a.s = 0.f; a.pad = 0; }
+    Partial a;                               // row `warp`: (max, argmax, sum-exp) over the whole vocabulary
+    if (lane < CL) a = s.part[lane][warp];
+    else { a.m = -INFINITY; a.idx = 0x7fffffff; a.s = 0.f; a.pad = 0; }
 #pragma unroll
-      for (int o = 1; o < CL; o <<= 1) {
-        Partial b = shfl_partial(a, o);
-        merge_partial(a, b);
-      }
-      const int tok = __shfl_sync(0xffffffffu, a.idx, 0);
+    for (int o = 1; o < CL; o <<= 1) {
+      Partial b = shfl_partial(a, o);
+      merge_partial(a, b);
+    }
+    int tok;
+    if constexpr (!BEAM) {
+      tok = __shfl_sync(0xffffffffu, a.idx, 0);
       if (c == 0 && lane == 0 && row_ok) {
         const int gr = row0 + warp;
         p.tokens[(size_t)gr * p.ld_tok + t + 1] = tok;
@@ -764,11 +885,87 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           if (cnt == p.rows) p.state->steps_executed = t + 1;      // src/inference.py:23-25
         }
       }
-      // ---- next input: embedding[token] + pos[t+1] ---------------------------------------------------
-      if (t + 1 < p.max_pos) embed_row(t + 1, tok);
+    } else {
+      // ---- beam step (oracle/decode.py::beam_search): candidates -> K best per image -> new hypotheses -----
+      xwait(X_TOP, ph_top, XB_TOP);
+      TopK<KB> tl;
+      if (lane < CL) tl.load(s.ctop[lane][warp]); else tl.init();
+#pragma unroll
+      for (int o = 1; o < CL; o <<= 1) tl.merge_xor(o);
+      if (lane == 0) {                       // candidates of hypothesis `warp`: score + log_softmax(logit)
+        const float lse = a.m + logf(a.s), sc = s.bscore[warp];
+        const bool fin = s.bfin[warp] != 0;
+        const int hyp = warp % p.beam;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          Cand cd;
+          cd.score = -INFINITY; cd.flat = 0x7fffffff;
+          if (row_ok && k < p.beam) {
+            if (fin) { if (k == 0) { cd.score = sc; cd.flat = hyp * p.vocab + p.pad; } }     // frozen: one candidate
+            else { cd.score = sc + (tl.v[k] - lse); cd.flat = hyp * p.vocab + tl.i[k]; }
+          }
+          s.cand[warp][k] = cd;
+        }
+      }
+      __syncthreads();
+      if (warp * p.beam < nrows) {           // warp i = image i of this cluster: K rounds of arg-best over K x KB candidates
+        const int hyp = lane / KB, k = lane - hyp * KB;
+        Cand cd;
+        cd.score = -INFINITY; cd.flat = 0x7fffffff;
+        if (hyp < p.beam) cd = s.cand[warp * p.beam + hyp][k];
+        for (int j = 0; j < p.beam; ++j) {
+          float bv = cd.score;
+          int bf = cd.flat;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+            if (cand_before(ov, of, bv, bf)) { bv = ov; bf = of; }
+          }
+          if (lane == 0) {
+            Sel se;
+            se.score = bv;
+            se.parent = (bf == 0x7fffffff) ? warp * p.beam : warp * p.beam + bf / p.vocab;
+            se.tok = (bf == 0x7fffffff) ? p.pad : bf % p.vocab;
+            s.sel[warp * p.beam + j] = se;
+          }
+          if (cd.flat == bf) { cd.score = -INFINITY; cd.flat = 0x7fffffff; }      // taken
+        }
+      }
+      __syncthreads();
+      const Sel me = s.sel[min(warp, nrows - 1)];
+      const int parent_fin = s.bfin[me.parent];
+      tok = me.tok;
+      __syncthreads();                       // every warp has read the old state
+      if (lane == 0 && row_ok) {
+        s.bscore[warp] = me.score;
+        s.bfin[warp] = parent_fin | (tok == p.eos);
+        s.bsrc[warp] = me.parent;
+        if (c == 0) {
+          p.bp_parent[(size_t)t * p.rows + row0 + warp] = me.parent % p.beam;     // clusters hold whole images
+          p.bp_token[(size_t)t * p.rows + row0 + warp] = tok;
+          p.bm_tok[row0 + warp] = tok;
+        }
+      }
     }
+    // ---- next input: embedding[token] + pos[t+1] ---------------------------------------------------
+    if (t + 1 < p.max_pos) embed_row(t + 1, tok);
     __syncthreads();
+    if (BEAM && tid == 0 && c == 0 && !cluster_done) {
+      bool all = true;
+      for (int r = 0; r < nrows; ++r) all = all && s.bfin[r] != 0;
+      if (all) {
+        cluster_done = true;
+        const int cnt = atomicAdd(&p.state->finished_count, 1) + 1;
+        if (cnt == p.num_clusters) p.state->steps_executed = t + 1;
+      }
+    }
     TR();
+  }
+  if (BEAM && c == 0 && tid < nrows) {       // hypothesis state back to HBM for the next launch / the back-track
+    p.bm_score[row0 + tid] = s.bscore[tid];
+    p.bm_fin[row0 + tid] = s.bfin[tid];
+    p.bm_src[row0 + tid] = s.bsrc[tid];
   }
   if (blockIdx.x == 0 && tid == 0) p.state->step = t_end;
   cluster_sync_all();      // no CTA exits while a peer may still address its shared memory
@@ -803,6 +1000,41 @@ __global__ void repack_memkv_kernel(const float* __restrict__ memkv, int images,
   }
 }
 
+__global__ void beam_init_kernel(DecodeState* state, float* bm_score, int* bm_fin, int* bm_src, int* bm_tok, int rows,
+                                 int beam, int rows_per_cluster, int sos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { state->step = 0; state->finished_count = 0; state->steps_executed = 0; state->pad_ = 0; }
+  if (i < rows) {
+    bm_score[i] = (i % beam == 0) ? 0.f : -INFINITY;     // all hypotheses start as [sos]: only the first one counts
+    bm_fin[i] = 0;
+    bm_src[i] = i % rows_per_cluster;
+    bm_tok[i] = sos;
+  }
+}
+
+__global__ void beam_finalize_kernel(const DecodeState* state, const float* bm_score, const int* bp_parent,
+                                     const int* bp_token, int images, int beam, int rows, int max_len, int sos, int pad,
+                                     int64_t* tokens, int ld_tok, float* score_out, int32_t* steps_out) {
+  const int steps = state->steps_executed > 0 ? state->steps_executed : min(state->step, max_len);
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img == 0 && steps_out != nullptr) *steps_out = steps;
+  if (img >= images) return;
+  int best = 0;
+  float bs = bm_score[img * beam];
+  for (int j = 1; j < beam; ++j)
+    if (bm_score[img * beam + j] > bs) { bs = bm_score[img * beam + j]; best = j; }       // first max
+  if (score_out != nullptr) score_out[img] = bs;
+  int64_t* out = tokens + (size_t)img * ld_tok;
+  out[0] = sos;
+  for (int k = steps + 1; k < ld_tok; ++k) out[k] = pad;
+  int b = best;
+  for (int t = steps - 1; t >= 0; --t) {
+    const size_t at = (size_t)t * rows + img * beam + b;
+    out[t + 1] = bp_token[at];
+    b = bp_parent[at];
+  }
+}
+
 int g_max_clusters = 0;
 
 }  // namespace
@@ -810,8 +1042,10 @@ int g_max_clusters = 0;
 int decode_persistent_init() {
   static bool done = false;
   if (done) return 0;
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, DP_MAX_BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, DP_MAX_BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL * 64);
   cfg.blockDim = dim3(THREADS);
@@ -820,7 +1054,7 @@ int decode_persistent_init() {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<5>, &cfg));
+  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<5, 0>, &cfg));
   HM_CHECK(g_max_clusters >= 1, "device cannot host an 8-CTA decode cluster");
   done = true;
   return 0;
@@ -839,13 +1073,42 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   HM_CHECK(p.fc_tiles % NW == 0 && p.fc_tiles > 0, "decode: bad fc_tiles %d", p.fc_tiles);
   HM_CHECK(p.chunks_per_step == DP_LAYER_CHUNKS * p.num_layers + p.fc_tiles, "decode: bad chunks_per_step");
   HM_CHECK(p.cache_blocks * 32 >= p.tmax, "decode: %d cache blocks cannot hold %d positions", p.cache_blocks, p.tmax);
-  // 8 rows per cluster; clusters are independent, so a batch larger than 8 x (co-resident clusters)
-  // simply runs in several waves.
-  dim3 grid(ceil_div(p.rows, R) * CL);
-  if (p.tmax <= 160)
-    decode_persistent_kernel<5><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
-  else
-    decode_persistent_kernel<8><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+  HM_CHECK(p.beam >= 1 && p.beam <= DP_MAX_BEAM, "decode: beam %d outside [1, %d]", p.beam, DP_MAX_BEAM);
+  const bool beam = p.beam > 1 || p.bm_score != nullptr;     // beam machinery (also runs beam = 1 for the A/B test)
+  // Rows per cluster: 8 (greedy) or whole images (beam).  Clusters are independent, so a batch larger than
+  // rows_per_cluster x (co-resident clusters) simply runs in several waves.
+  if (beam) {
+    HM_CHECK(p.rows_per_cluster == p.beam * (R / p.beam) && p.rows % p.beam == 0, "decode: bad beam geometry");
+    HM_CHECK(p.bm_score && p.bm_fin && p.bm_src && p.bm_tok && p.bp_parent && p.bp_token, "decode: beam buffers missing");
+  } else {
+    p.rows_per_cluster = R;
+  }
+  p.num_clusters = ceil_div(p.rows, p.rows_per_cluster);
+  dim3 grid(p.num_clusters * CL);
+  if (p.tmax <= 160) {
+    if (beam) decode_persistent_kernel<5, DP_MAX_BEAM><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    else decode_persistent_kernel<5, 0><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+  } else {
+    if (beam) decode_persistent_kernel<8, DP_MAX_BEAM><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    else decode_persistent_kernel<8, 0><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+  }
+  HM_LAUNCHED();
+  return 0;
+}
+
+int beam_init(cudaStream_t st, DecodeState* state, float* bm_score, int* bm_fin, int* bm_src, int* bm_tok, int rows,
+              int beam, int rows_per_cluster, int sos) {
+  beam_init_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(state, bm_score, bm_fin, bm_src, bm_tok, rows, beam,
+                                                        rows_per_cluster, sos);
+  HM_LAUNCHED();
+  return 0;
+}
+
+int beam_finalize(cudaStream_t st, const DecodeState* state, const float* bm_score, const int* bp_parent,
+                  const int* bp_token, int images, int beam, int rows, int max_len, int sos, int pad, int64_t* tokens,
+                  int ld_tok, float* score_out, int32_t* steps_out) {
+  beam_finalize_kernel<<<ceil_div(images, 128), 128, 0, st>>>(state, bm_score, bp_parent, bp_token, images, beam, rows,
+                                                              max_len, sos, pad, tokens, ld_tok, score_out, steps_out);
   HM_LAUNCHED();
   return 0;
 }

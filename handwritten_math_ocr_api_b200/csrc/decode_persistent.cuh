@@ -44,8 +44,22 @@ struct DecPersistParams {
   uint8_t* finished;          // [rows]
   DecodeState* state;
   int rows, images, beam;     // rows = images * beam; row r reads the memory of image r / beam
+  // ---- beam search (beam > 1; the reference has none - definition in oracle/decode.py::beam_search) ----
+  // A cluster owns floor(8 / beam) images = rows_per_cluster rows.  The K/V caches exist twice: step t reads the
+  // history of hypothesis j from set (t & 1), row bm_src[j] (its parent's row), and writes history + this step's
+  // key/value to set ((t + 1) & 1), row j - the parent gather rides on the attention loads, nothing is copied
+  // separately.  Per step the chosen (parent, token) of every row is recorded for the final back-track.
+  int rows_per_cluster;       // 8 (greedy) or beam * (8 / beam)
+  int num_clusters;
+  size_t cache_set_stride;    // halves between the two cache sets (0 in greedy mode)
+  float* bm_score;            // [rows] summed log-probability of each live hypothesis
+  int* bm_fin;                // [rows] hypothesis has emitted eos
+  int* bm_src;                // [rows] cluster-local row that holds the hypothesis' history in the current set
+  int* bm_tok;                // [rows] token fed at the next step
+  int* bp_parent;             // [max_len][rows] beam index (within the image) of the parent chosen at step t
+  int* bp_token;              // [max_len][rows] token chosen at step t
   int num_layers, fc_tiles, chunks_per_step, vocab;
-  int tmax, max_pos, max_len, ld_tok, eos;
+  int tmax, max_pos, max_len, ld_tok, eos, pad;
   long long* trace;           // optional: clock64() of cluster 0 / CTA 0 / thread 0 at every phase boundary
   int trace_step;             //           of decode step `trace_step`
   int flags;                  // developer switches: 1 = no L2 prefetch of the next layer's cache, 2 = none of the memory K/V
@@ -56,5 +70,13 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
 int decode_persistent_max_clusters(int* out);   // co-resident clusters on this device
 // memkv f32 [img*30+s][l*512 + kv*256 + h*32 + d] -> the fp16 memk / memv layouts above
 int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, void* memk, void* memv);
+constexpr int DP_MAX_BEAM = 5;
+// beam search bookkeeping around the persistent kernel
+int beam_init(cudaStream_t st, DecodeState* state, float* bm_score, int* bm_fin, int* bm_src, int* bm_tok, int rows,
+              int beam, int rows_per_cluster, int sos);
+// best hypothesis per image (highest score, ties -> lowest beam index), back-tracked through bp_parent / bp_token
+int beam_finalize(cudaStream_t st, const DecodeState* state, const float* bm_score, const int* bp_parent,
+                  const int* bp_token, int images, int beam, int rows, int max_len, int sos, int pad, int64_t* tokens,
+                  int ld_tok, float* score_out, int32_t* steps_out);
 
 }  // namespace hmocr

@@ -86,6 +86,7 @@ struct hmocr_engine {
   int steps_per_launch = 16;
   int trace_step = -1;                // >= 0: record phase-boundary clocks of that decode step
   int dbg_flags = 0;                  // DecPersistParams::flags
+  int force_beam_kernel = 0;          // run beam = 1 through the beam-search kernel (A/B test against greedy)
 
   // scratch (grow-only); any reallocation invalidates the captured step graphs
   std::map<std::string, Buf> ws;
@@ -376,16 +377,16 @@ int enqueue_step(hmocr_engine* e, const GenBufs& g, int rows, const h16* memkv, 
   return 0;
 }
 
-int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, int64_t* tokens,
-                        float* logprob, int32_t* steps, cudaStream_t st);
+int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, int beam, int64_t* tokens,
+                        float* logprob, int32_t* steps, float* score, cudaStream_t st);
 
 int generate_from_memory_impl(hmocr_engine* e, const h16* enc16, int B, int max_len, int beam,
                               int64_t* tokens, float* logprob, int32_t* steps, float* score, cudaStream_t st) {
-  HM_CHECK(beam == 1, "beam search (beam=%d) is not built yet in this round: only greedy (beam=1)", beam);
   HM_CHECK(max_len >= 1 && max_len <= e->cfg.max_seq_len,
            "max_len=%d outside [1, %d] (size of pos_encoder, src/model_swin.py:54)", max_len, e->cfg.max_seq_len);
-  (void)score;
-  if (e->decode_impl == 0) return generate_persistent(e, enc16, B, max_len, tokens, logprob, steps, st);
+  HM_CHECK(beam >= 1 && beam <= DP_MAX_BEAM, "beam=%d outside [1, %d]", beam, DP_MAX_BEAM);
+  if (e->decode_impl == 0) return generate_persistent(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st);
+  HM_CHECK(beam == 1, "the step-graph decode (decode_impl=1) is greedy only; beam=%d needs decode_impl=0", beam);
   const int d = e->cfg.d_model, nh = e->cfg.nhead, L = e->cfg.num_layers;
   const int rows = B;
   h16* memkv;
@@ -536,11 +537,15 @@ int pack_decode_operands(hmocr_engine* e) {
   return 0;
 }
 
-// greedy decode with the persistent cluster kernel: a few launches of `steps_per_launch` steps, the
-// host only polls the all-finished flag of the PREVIOUS launch (the GPU never idles)
-int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, int64_t* tokens,
-                        float* logprob, int32_t* steps, cudaStream_t st) {
-  const int nh = e->cfg.nhead, L = e->cfg.num_layers, rows = B;
+// decode with the persistent cluster kernel: a few launches of `steps_per_launch` steps, the host only polls
+// the all-finished flag of the PREVIOUS launch (the GPU never idles).  beam == 1: greedy
+// (src/inference.py:15-25).  beam > 1 (or option "force_beam_kernel"): beam search as defined in
+// oracle/decode.py::beam_search - rows = images x beam hypotheses, two K/V cache sets, back-track at the end.
+int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, int beam, int64_t* tokens,
+                        float* logprob, int32_t* steps, float* score, cudaStream_t st) {
+  const int nh = e->cfg.nhead, L = e->cfg.num_layers, rows = B * beam;
+  const bool beam_mode = beam > 1 || e->force_beam_kernel;
+  HM_CHECK(beam >= 1 && beam <= DP_MAX_BEAM, "beam=%d outside [1, %d]", beam, DP_MAX_BEAM);
   float* memkv;                       // memory K/V of all layers, fp32 out of the GEMM, fp16 after the repack
   __half *memk, *memv, *kcache, *vcache;
   DecodeState* state;
@@ -549,15 +554,16 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   HM_TRY(ws_get(e, "dp.memkv32", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
   HM_TRY(ws_get(e, "dp.memk", (size_t)L * B * nh * 1024, &memk));
   HM_TRY(ws_get(e, "dp.memv", (size_t)L * B * nh * 1024, &memv));
+  const size_t set_elems = (size_t)L * rows * nh * cache_blocks * 1024;
   {
     // whole 32-key blocks are read: the unwritten tail of a block must always hold finite numbers
-    const size_t elems = (size_t)L * rows * nh * cache_blocks * 1024;
+    const size_t elems = set_elems * (beam_mode ? 2 : 1);
     uint64_t epoch = e->ws_epoch;
     HM_TRY(ws_get(e, "dp.kcache", elems, &kcache));
-    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(kcache, 0, elems * sizeof(__half), st));
+    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(kcache, 0, e->ws["dp.kcache"].cap, st));
     epoch = e->ws_epoch;
     HM_TRY(ws_get(e, "dp.vcache", elems, &vcache));
-    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(vcache, 0, elems * sizeof(__half), st));
+    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(vcache, 0, e->ws["dp.vcache"].cap, st));
   }
   HM_TRY(ws_get(e, "gen.state", 1, &state));
   HM_TRY(ws_get(e, "gen.finished", rows, &finished));
@@ -567,17 +573,31 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
     HM_TRY(run_lin(st, enc16, e->cfg.d_model, B * MEM_S, e->ca_kv, ek));
   }
   HM_TRY(repack_memkv(st, memkv, B, L, memk, memv));
-  HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   DecPersistParams p;
+  memset(&p, 0, sizeof(p));
   p.wstream = e->dp_wstream;
   p.lnparams = e->dp_lnparams;
   p.emb = e->emb; p.pos = e->pos; p.kcache = kcache; p.vcache = vcache; p.memk = memk; p.memv = memv;
   p.tokens = tokens; p.logprob = logprob; p.finished = finished; p.state = state;
-  p.rows = rows; p.images = B; p.beam = 1; p.num_layers = L; p.fc_tiles = e->dp_fc_tiles;
+  p.rows = rows; p.images = B; p.beam = beam; p.num_layers = L; p.fc_tiles = e->dp_fc_tiles;
   p.chunks_per_step = e->dp_chunks_per_step;
   p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
-  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id; p.cache_blocks = cache_blocks;
+  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id; p.pad = e->cfg.pad_id; p.cache_blocks = cache_blocks;
   p.trace = nullptr; p.trace_step = e->trace_step; p.flags = e->dbg_flags;
+  p.rows_per_cluster = DP_ROWS;
+  if (beam_mode) {
+    p.rows_per_cluster = beam * (DP_ROWS / beam);
+    p.cache_set_stride = set_elems;
+    HM_TRY(ws_get(e, "bm.score", rows, &p.bm_score));
+    HM_TRY(ws_get(e, "bm.fin", rows, &p.bm_fin));
+    HM_TRY(ws_get(e, "bm.src", rows, &p.bm_src));
+    HM_TRY(ws_get(e, "bm.tok", rows, &p.bm_tok));
+    HM_TRY(ws_get(e, "bm.parent", (size_t)max_len * rows, &p.bp_parent));
+    HM_TRY(ws_get(e, "bm.token", (size_t)max_len * rows, &p.bp_token));
+    HM_TRY(beam_init(st, state, p.bm_score, p.bm_fin, p.bm_src, p.bm_tok, rows, beam, p.rows_per_cluster, e->cfg.sos_id));
+  } else {
+    HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
+  }
   if (e->trace_step >= 0) {
     HM_TRY(ws_get(e, "gen.trace", 1024, &p.trace));
     HM_CUDA(cudaMemsetAsync(p.trace, 0, 1024 * sizeof(long long), st));
@@ -597,7 +617,13 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
       if (e->pinned_state[prev].steps_executed > 0) done = true;
     }
   }
-  HM_TRY(finalize_decode(st, state, tokens, max_len + 1, rows, max_len, e->cfg.pad_id, logprob, steps));
+  if (beam_mode) {
+    HM_TRY(beam_finalize(st, state, p.bm_score, p.bp_parent, p.bp_token, B, beam, rows, max_len, e->cfg.sos_id,
+                         e->cfg.pad_id, tokens, max_len + 1, score, steps));
+    if (logprob != nullptr) HM_CUDA(cudaMemsetAsync(logprob, 0, sizeof(float) * B * max_len, st));
+  } else {
+    HM_TRY(finalize_decode(st, state, tokens, max_len + 1, rows, max_len, e->cfg.pad_id, logprob, steps));
+  }
   return 0;
 }
 
@@ -810,6 +836,8 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     e->trace_step = value;
   } else if (n == "dbg_flags") {
     e->dbg_flags = value;
+  } else if (n == "force_beam_kernel") {
+    e->force_beam_kernel = value != 0;
   } else {
     HM_CHECK(false, "unknown option '%s'", name);
   }

@@ -63,7 +63,8 @@ int hmocr_finalize_weights(hmocr_engine* e);
 /* Engine options (all have working defaults):
  *   "decode_impl"       0 = persistent thread-block-cluster decode kernel (default)
  *                       1 = one captured CUDA graph of per-layer kernels per step (kept for A/B tests)
- *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16) */
+ *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16)
+ *   "force_beam_kernel" 1 = run beam == 1 through the beam-search kernel (A/B test against greedy) */
 int hmocr_set_option(hmocr_engine* e, const char* name, int value);
 /* Developer aid: with option "trace_step" = t >= 0 the persistent decode kernel records clock64()
  * of (cluster 0, CTA 0, thread 0) at every phase boundary of decode step t; this copies the first
@@ -90,8 +91,10 @@ int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out_dev, const int64
  *   steps_dev    int32 [1]             number of decode steps executed = ys.shape[1]-1 of the
  *                                      reference (stops when every row has emitted eos)
  * beam == 1: greedy, finished rows keep decoding exactly as the reference does.
- * beam  > 1: beam search as defined in DESIGN.md (the reference has none); tokens are the best
- *            hypothesis per image, score_dev f32 [B] its summed log-probability (may be NULL). */
+ * beam  > 1: beam search (2..5 hypotheses per image) as defined in DESIGN.md section 4.6 - the reference
+ *            has none, `beam_size` is an unused parameter of src/inference.py:7; tokens are the best
+ *            hypothesis per image (finished hypotheses are padded), score_dev f32 [B] its summed
+ *            log-probability (may be NULL); logprob_dev is zero-filled. */
 int hmocr_generate(hmocr_engine* e, const float* images_dev, int batch, int max_len, int beam, int64_t* tokens_dev,
                    float* logprob_dev, int32_t* steps_dev, float* score_dev, void* stream);
 

@@ -302,3 +302,70 @@ def test_greedy_agreement_on_a_larger_sample(model, sd, cfg):
           f"max {max(div_margins) if div_margins else 0:.4f}, median {float(np.median(div_margins)) if div_margins else 0:.4f}")
     assert err < DECODE_LOGP_TOL
     assert same >= 48
+
+
+# ---- beam search (not in the reference: SURVEY.md D2; definition + oracle in oracle/decode.py::beam_search) -------
+def _oracle_sequence_score(enc, tokens, sd, cfg):
+    """Sum of the oracle's log-softmax over the emitted tokens of each row, up to and including the first eos."""
+    from oracle.ref_model import decoder_forward
+    with torch.no_grad():
+        lsm = torch.log_softmax(decoder_forward(enc, tokens[:, :-1], sd, cfg).float(), -1)
+    out = []
+    for r in range(tokens.shape[0]):
+        s = 0.0
+        for t in range(1, tokens.shape[1]):
+            tk = int(tokens[r, t])
+            s += float(lsm[r, t - 1, tk])
+            if tk == cfg.eos:
+                break
+        out.append(s)
+    return torch.tensor(out)
+
+
+def test_beam_kernel_with_one_hypothesis_equals_greedy(model, cfg, golden_src):
+    """beam = 1 pushed through the beam-search machinery (top-K lists, candidate merge, parent back-track, two
+    cache sets) must reproduce the greedy kernel token for token up to each row's eos."""
+    feats = torch.from_numpy(golden_src["features"]).cuda()
+    g_tok, g_steps, _ = model.generate(encoder_out=feats, max_len=48)
+    model.set_option("force_beam_kernel", 1)
+    try:
+        b_tok, b_steps, _ = model.generate(encoder_out=feats, max_len=48)
+    finally:
+        model.set_option("force_beam_kernel", 0)
+    assert b_steps == g_steps
+    for r in range(feats.shape[0]):
+        row = g_tok[r].tolist()
+        n = row.index(cfg.eos) + 1 if cfg.eos in row else len(row)
+        assert b_tok[r, :n].tolist() == row[:n]
+        assert all(int(x) == cfg.pad for x in b_tok[r, n:])          # finished hypotheses emit pad
+
+
+@pytest.mark.parametrize("beam", [2, 3, 5])
+def test_beam_search_against_the_oracle(model, sd, cfg, golden_src, beam):
+    from oracle import decode as odec
+    feats = torch.from_numpy(golden_src["features"][:3]).cuda()
+    tokens, steps, _, score = model.generate(encoder_out=feats, beam_size=beam, max_len=40)
+    assert tokens.shape == (3, steps + 1) and score.shape == (3,)
+    enc = feats.cpu()
+    o_tok, o_score, _, _ = odec.beam_search(enc, sd, cfg, beam=beam, max_len=40)
+    # (1) the score we report is the oracle's log-probability of the sequence we return (scoring + back-track)
+    mine = _oracle_sequence_score(enc, tokens.cpu(), sd, cfg)
+    assert (mine - score.cpu()).abs().max().item() < 3e-2
+    # (2) same search result as the oracle: identical best score up to near-tie path changes
+    print("beam", beam, "scores", score.cpu().tolist(), "oracle", o_score.tolist())
+    assert (score.cpu() - o_score).abs().max().item() < 5e-2
+    same = sum(int(tokens[r, : o_tok.shape[1]].cpu().tolist() == o_tok[r, : tokens.shape[1]].tolist()) for r in range(3))
+    print("identical best hypotheses:", same, "/ 3")
+    # (3) a wider beam never returns a worse hypothesis than greedy (beam search invariant on these inputs)
+    g_tok, _, _ = model.generate(encoder_out=feats, max_len=40)
+    greedy = _oracle_sequence_score(enc, g_tok.cpu(), sd, cfg)
+    assert (score.cpu() >= greedy - 3e-2).all()
+
+
+def test_beam_search_is_batch_invariant(model, golden_src):
+    feats = torch.from_numpy(golden_src["features"]).cuda()
+    all_tok, steps, _, all_score = model.generate(encoder_out=feats, beam_size=5, max_len=30)
+    for i in range(feats.shape[0]):
+        one, s1, _, sc = model.generate(encoder_out=feats[i:i + 1], beam_size=5, max_len=30)
+        n = min(one.shape[1], all_tok.shape[1])
+        assert torch.equal(one[0, :n], all_tok[i, :n]) and abs(float(sc[0]) - float(all_score[i])) < 1e-5
