@@ -836,6 +836,8 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     e->trace_step = value;
   } else if (n == "dbg_flags") {
     e->dbg_flags = value;
+  } else if (n == "gemm_dbg") {
+    gemm_set_debug(value);
   } else if (n == "force_beam_kernel") {
     e->force_beam_kernel = value != 0;
   } else {

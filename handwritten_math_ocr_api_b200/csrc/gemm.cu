@@ -30,26 +30,29 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int NUM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 320;
 
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 32 * 4;      // one 32 x 32 fp32 transpose tile per epilogue warp
+  static constexpr int STAGES_RAW = (190 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_STAGE_BYTES;
 };
 
 struct GemmParams {
   int M, N, K;
   int num_n_tiles, num_tiles;
+  int dbg;            // timing experiments only: 1 = skip output stores, 2 = skip residual loads
   GemmEpilogue epi;
 };
+int g_gemm_dbg = 0;
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (8-row x 128B atoms, 1024B apart).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -71,52 +74,59 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
          | (uint32_t(BM >> 4) << 24);  // M
 }
 
+// Plain epilogue of one 32-row x BN-column slab (this warp's TMEM lane quarter), 32 columns at a time.
+// tcgen05.ld hands every thread one ROW (32 consecutive fp32 of it); global memory wants the opposite: a warp
+// instruction that covers whole rows.  So the raw accumulators go through a 4 KB per-warp shared tile
+// (16-byte chunks XOR-swizzled by row: conflict-free both ways) and come back with lane = (row % 4, 4-column
+// group): every load of the fp32 residual and every store is 4 rows x 128 contiguous bytes (fp16: x 64) instead
+// of 32 scattered 16-byte pieces.  Bias, activation and residual are applied in that second layout, where a
+// lane owns the same 4 columns for all 32 rows (one bias load per chunk).  The residual loads are issued before
+// the TMEM load so their latency overlaps it.
 template <int BN>
-__device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t taddr, int row, bool row_ok,
-                                               int n0, int c_first) {
+__device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t taddr, float* stage, int m_base,
+                                               int M, int n0, int c_first, int dbg) {
+  const int lane = threadIdx.x & 31;
+  const int rr = lane >> 3, cg = lane & 7;            // second layout: row (it*4 + rr), columns 4*cg .. 4*cg+3
+  const uint32_t st_addr = smem_u32(stage);
 #pragma unroll 1
   for (int c = c_first; c < BN / 32; c += 2) {
+    const int col = n0 + c * 32 + cg * 4;
+    float4 res[8];
+    const bool has_res = e.residual != nullptr && !(dbg & 2);
+    if (has_res) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = m_base + it * 4 + rr;
+        res[it] = (row < M) ? __ldcs(reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
     uint32_t r[32];
     tmem_ld32(taddr + c * 32, r);
-    const int col = n0 + c * 32;
-    float v[32];
+    __syncwarp();                                      // the previous chunk has been read out of the tile
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (e.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+    for (int q = 0; q < 8; ++q)                        // thread = row `lane`: chunk q -> physical chunk q ^ (lane & 7)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + lane * 128 + ((q ^ (lane & 7)) << 4)),
+                   "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+                   : "memory");
+    __syncwarp();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 b = __ldg(b4 + q);
-        v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-      }
-    }
-    if (e.act == 1) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    } else if (e.act == 2) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-    }
-    if (row_ok) {
-      if (e.residual != nullptr) {
-        const float4* r4 = reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 x = r4[q];
-          v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
-        }
-      }
-      if (e.out_f32 != nullptr) {
-        float4* o = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld32 + col);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      if (e.out_f16 != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(e.out_f16 + (size_t)row * e.ld16 + col);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          o[q] = make_uint4(pack16(v[8 * q], v[8 * q + 1]), pack16(v[8 * q + 2], v[8 * q + 3]),
-                            pack16(v[8 * q + 4], v[8 * q + 5]), pack16(v[8 * q + 6], v[8 * q + 7]));
+    for (int it = 0; it < 8; ++it) {
+      const int lr = it * 4 + rr, row = m_base + lr;
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(st_addr + lr * 128 + ((cg ^ (lr & 7)) << 4)));
+      v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+      if (e.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+      else if (e.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+      if (row < M && !((dbg & 1) && v.x != 12345.678f)) {
+        if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld32 + col) = v;
+        if (e.out_f16 != nullptr)
+          *reinterpret_cast<uint2*>(e.out_f16 + (size_t)row * e.ld16 + col) = make_uint2(pack16(v.x, v.y), pack16(v.z, v.w));
       }
     }
   }
@@ -209,6 +219,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);   // 1024-aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -295,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.epi.ln_gamma != nullptr) {
         if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row_ok, n0);     // row statistics: one thread per row
       } else {
-        epilogue_plain<BN>(p.epi, taddr, row, row_ok, n0, half);
+        epilogue_plain<BN>(p.epi, taddr, epi_stage + (warp - 2) * 1024, m0 + quarter * 32, p.M, n0, half, p.dbg);
       }
       tc_fence_before();
       __syncwarp();
@@ -358,6 +369,7 @@ int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* 
   p.num_n_tiles = N / BN;
   p.num_tiles = ceil_div(M, BM) * p.num_n_tiles;
   p.epi = epi;
+  p.dbg = g_gemm_dbg;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
   HM_LAUNCHED();
@@ -365,6 +377,8 @@ int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* 
 }
 
 }  // namespace
+
+void gemm_set_debug(int v) { g_gemm_dbg = v; }
 
 int gemm_init() {
   std::lock_guard<std::mutex> lk(g_mu);

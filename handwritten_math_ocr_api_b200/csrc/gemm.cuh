@@ -24,6 +24,7 @@ struct GemmEpilogue {
 int gemm_f16(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* W,
               int N, const GemmEpilogue& epi, int force_bn = 0);
 
-int gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
+int gemm_init();
+void gemm_set_debug(int v);   // timing experiments only (see gemm.cu)   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
 
 }  // namespace hmocr
