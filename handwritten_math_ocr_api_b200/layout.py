@@ -103,3 +103,58 @@ def state_dict_layout(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]
             out += [(p + n + ".weight", (d,), f32), (p + n + ".bias", (d,), f32)]
     out += [("decoder.fc_out.weight", (v, d), f32), ("decoder.fc_out.bias", (v,), f32)]
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# ResNet-18 + TransformerEncoder variant (/root/reference/src/model_res18trans.py, BASELINE.json config 4)
+# ------------------------------------------------------------------------------------------------
+RES18_MEM_TOKENS = 10             # [B,512,3,10] -> AdaptiveAvgPool (1,None) -> 10 memory tokens
+RES18_STAGES = ((64, 1), (128, 2), (256, 2), (512, 2))     # (channels, stride of the first block) of layer1..4
+
+
+def _bn_keys(p: str, c: int):
+    f32 = "float32"
+    return [(p + ".weight", (c,), f32), (p + ".bias", (c,), f32), (p + ".running_mean", (c,), f32),
+            (p + ".running_var", (c,), f32), (p + ".num_batches_tracked", (), "int64")]
+
+
+def state_dict_layout_res18(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """The 367 (name, shape, dtype) entries of model_res18trans.FormulaRecognitionModel(V).state_dict()
+    in the reference's own order (checked against the live reference by oracle/make_golden_res18.py)."""
+    f32 = "float32"
+    out: List[Tuple[str, Tuple[int, ...], str]] = []
+    f = "encoder.features."
+    out += [(f + "0.weight", (64, 1, 7, 7), f32)] + _bn_keys(f + "1", 64)
+    cin = 64
+    for s, (c, stride) in enumerate(RES18_STAGES):
+        for j in range(2):
+            p = f"{f}{4 + s}.{j}."
+            out += [(p + "conv1.weight", (c, cin if j == 0 else c, 3, 3), f32)] + _bn_keys(p + "bn1", c)
+            out += [(p + "conv2.weight", (c, c, 3, 3), f32)] + _bn_keys(p + "bn2", c)
+            if j == 0 and (stride != 1 or cin != c):
+                out += [(p + "downsample.0.weight", (c, cin, 1, 1), f32)] + _bn_keys(p + "downsample.1", c)
+        cin = c
+    d, ff, v = cfg.d_model, cfg.dim_feedforward, cfg.vocab_size
+    out += [("encoder.projection.weight", (d, 512), f32), ("encoder.projection.bias", (d,), f32)]
+    for l in range(cfg.num_layers):
+        p = f"encoder.transformer_encoder.layers.{l}."
+        out += [(p + "self_attn.in_proj_weight", (3 * d, d), f32), (p + "self_attn.in_proj_bias", (3 * d,), f32),
+                (p + "self_attn.out_proj.weight", (d, d), f32), (p + "self_attn.out_proj.bias", (d,), f32),
+                (p + "linear1.weight", (ff, d), f32), (p + "linear1.bias", (ff,), f32),
+                (p + "linear2.weight", (d, ff), f32), (p + "linear2.bias", (d,), f32)]
+        for n in ("norm1", "norm2"):
+            out += [(p + n + ".weight", (d,), f32), (p + n + ".bias", (d,), f32)]
+    out += [("decoder.tgt_mask", (cfg.max_seq_len, cfg.max_seq_len), f32),
+            ("decoder.embedding.weight", (v, d), f32),
+            ("decoder.pos_encoder.weight", (cfg.max_seq_len, d), f32)]
+    for l in range(cfg.num_layers):
+        p = f"decoder.transformer_decoder.layers.{l}."
+        for att in ("self_attn", "multihead_attn"):
+            out += [(p + att + ".in_proj_weight", (3 * d, d), f32), (p + att + ".in_proj_bias", (3 * d,), f32),
+                    (p + att + ".out_proj.weight", (d, d), f32), (p + att + ".out_proj.bias", (d,), f32)]
+        out += [(p + "linear1.weight", (ff, d), f32), (p + "linear1.bias", (ff,), f32),
+                (p + "linear2.weight", (d, ff), f32), (p + "linear2.bias", (d,), f32)]
+        for n in ("norm1", "norm2", "norm3"):
+            out += [(p + n + ".weight", (d,), f32), (p + n + ".bias", (d,), f32)]
+    out += [("decoder.fc_out.weight", (v, d), f32), ("decoder.fc_out.bias", (v,), f32)]
+    return out

@@ -23,7 +23,8 @@ from typing import Dict
 import numpy as np
 import torch
 
-from .layout import IMG_H, IMG_W, WINDOW, ModelConfig, state_dict_layout
+from .layout import (IMG_H, IMG_W, RES18_MEM_TOKENS, WINDOW, ModelConfig, state_dict_layout,
+                     state_dict_layout_res18)
 
 _M64 = (1 << 64) - 1
 
@@ -117,6 +118,48 @@ def synth_state_dict(cfg: ModelConfig | None = None, seed: int = 0, fc_gain: flo
     if eos_bias_sigma:
         sd["decoder.fc_out.bias"][cfg.eos] += float(eos_bias_sigma) * fc_gain
     return sd
+
+
+def synth_state_dict_res18(cfg: ModelConfig | None = None, seed: int = 0, fc_gain: float = 4.0,
+                           eos_bias_sigma: float = 2.5) -> Dict[str, torch.Tensor]:
+    """Synthetic checkpoint in the 367-entry layout of /root/reference/src/model_res18trans.py.
+    Conv weights are He-scaled, BatchNorm running statistics non-trivial (mean ~ U(-0.2,0.2), var ~ U(0.5,1.5))."""
+    cfg = cfg or ModelConfig()
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape, dtype in state_dict_layout_res18(cfg):
+        leaf = name.rsplit(".", 1)[-1]
+        if name == "decoder.tgt_mask":
+            sd[name] = torch.triu(torch.full((cfg.max_seq_len, cfg.max_seq_len), float("-inf")), diagonal=1)
+            continue
+        if leaf == "num_batches_tracked":
+            sd[name] = torch.tensor(1000, dtype=torch.int64)
+            continue
+        n = int(np.prod(shape))
+        u = _uniform(name, n, seed)
+        if leaf == "running_var":
+            vals = 1.0 + 0.5 * u
+        elif leaf == "running_mean":
+            vals = 0.2 * u
+        elif len(shape) == 4:                                   # conv: He-uniform on fan_in
+            fan_in = int(np.prod(shape[1:]))
+            vals = math.sqrt(6.0 / fan_in) * u
+        elif ".bn" in name or "downsample.1" in name or name.startswith("encoder.features.1."):
+            vals = (1.0 + 0.2 * u) if leaf == "weight" else 0.1 * u
+        else:
+            key = name.replace("decoder.transformer_decoder.", "decoder.decoder.")
+            scale, offset = _scale_for(key, shape, cfg, fc_gain)
+            vals = offset + scale * u
+        sd[name] = torch.from_numpy(np.asarray(vals, dtype=np.float32).reshape(shape))
+    if eos_bias_sigma:
+        sd["decoder.fc_out.bias"][cfg.eos] += float(eos_bias_sigma) * fc_gain
+    return sd
+
+
+def synth_pos_table(d_model: int = 256, seed: int = 0) -> torch.Tensor:
+    """Stand-in for the nn.Embedding(10, d_model) the reference re-creates (N(0,1)-initialised) on EVERY encoder
+    call (src/model_res18trans.py:57-59): the table is an explicit input of the engine."""
+    u = _uniform("res18trans.pos_embed", RES18_MEM_TOKENS * d_model, seed)
+    return torch.from_numpy((math.sqrt(3.0) * u).astype(np.float32).reshape(RES18_MEM_TOKENS, d_model))
 
 
 def state_dict_checksum(sd: Dict[str, torch.Tensor]) -> str:

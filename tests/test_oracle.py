@@ -142,3 +142,40 @@ def test_beam_invariants(sd, cfg, golden_src):
 def test_clean_latex_output():
     assert odec.clean_latex_output(r"\begin {matrix} a \end {matrix}") == r"\begin{matrix} a \end{matrix}"
     assert odec.clean_latex_output(r"\mathrm { abc }") == r"\mathrm {abc}"
+
+
+# ---- ResNet-18 + TransformerEncoder variant (BASELINE.json config 4) --------------------------------------
+def test_res18_oracle_against_reference_golden():
+    """oracle/res18_model.py reproduces the outputs the unmodified /root/reference/src/model_res18trans.py
+    produced for the same synthetic checkpoint, images and positional table (oracle/make_golden_res18.py)."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+
+    from handwritten_math_ocr_api_b200.layout import ModelConfig, state_dict_layout_res18
+    from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_pos_table, synth_state_dict_res18
+    from oracle import res18_model as R
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "res18_golden.npz"))
+    cfg = ModelConfig()
+    sd = synth_state_dict_res18(cfg, seed=int(gold["weights_seed"]))
+    manifest = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "res18_state_dict_manifest.json")))
+    assert [(k, list(s), d) for k, s, d in state_dict_layout_res18(cfg)] == [tuple(e) if False else (e[0], e[1], e[2])
+                                                                            for e in manifest["entries"]]
+    assert len(manifest["entries"]) == 367
+    imgs = synth_images(4, int(gold["images_seed"]))
+    pos = synth_pos_table(cfg.d_model, seed=0)
+    assert np.array_equal(pos.numpy(), gold["pos_table"])
+    with torch.no_grad():
+        assert np.abs(R.trunk(imgs, sd).numpy() - gold["trunk"]).max() < 1e-2          # activations up to ~330
+        feats = R.encoder_forward(imgs, sd, cfg, pos)
+        assert np.abs(feats.numpy() - gold["features"]).max() < 1e-4
+        logits = R.decoder_forward(torch.from_numpy(gold["features"]), torch.from_numpy(gold["tgt"]), sd, cfg)
+        assert np.abs(logits.numpy() - gold["logits"]).max() < 1e-3
+        ys = R.greedy_cached(torch.from_numpy(gold["features"]), sd, cfg, max_len=40)
+        assert np.array_equal(ys.numpy(), gold["greedy_ys"])
+        # SURVEY.md D7: the encoder attends across the batch - an image's features depend on its batch-mates
+        alone = R.encoder_forward(imgs[1:2], sd, cfg, pos)
+        assert (alone - feats[1:2]).abs().max().item() > 1e-2
