@@ -15,6 +15,8 @@ class Config:
     dropout = 0.2                      # identity in eval; the engine is inference-only
     swin_num_decoder_layers = 8        # src/config.py:32
     num_decoder_layers = 8             # app/src/config.py:27
+    res18trans_num_encoder_layers = 8  # src/config.py:28
+    res18trans_num_decoder_layers = 8  # src/config.py:29
     max_seq_len = 150
     sos_token = '<sos>'
     eos_token = '<eos>'

@@ -47,7 +47,7 @@ namespace hmocr {
 namespace {
 
 constexpr int CL = 8, THREADS = 256, NW = 8, R = DP_ROWS;
-constexpr int D = 256, FF = 512, HD = 32, NH = 8, MEM_S = 30;
+constexpr int D = 256, FF = 512, HD = 32, NH = 8;
 constexpr int PD = D + 8, PF = FF + 8;            // padded operand pitches (elements): conflict-free ldmatrix
 constexpr float ATT_SCALE = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32): softmax on ex2
 constexpr float LN_EPS = 1e-5f;
@@ -710,12 +710,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         }
         g += 2;
       }
-      attend_issue<1>(Mk, MEM_S, lane, kv);
+      attend_issue<1>(Mk, p.mem_len, lane, kv);
       __syncthreads();
       TR();
       {
         float o[4];
-        attend_mma<1, false, false>(&s.qh[warp][0], Mk, Mv, MEM_S, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
+        attend_mma<1, false, false>(&s.qh[warp][0], Mk, Mv, p.mem_len, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
         send_ctx(o);
       }
       TR();
@@ -971,7 +971,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   cluster_sync_all();      // no CTA exits while a peer may still address its shared memory
 }
 
-__global__ void repack_memkv_kernel(const float* __restrict__ memkv, int images, int L,
+__global__ void repack_memkv_kernel(const float* __restrict__ memkv, int images, int L, int MEM_S,
                                     __half* __restrict__ memk, __half* __restrict__ memv) {
   // memkv f32 [img*30+s][l*512 + kv*256 + h*32 + d]  ->  one fragment-major block (32 key slots, keys 30 and 31
   // zero) of memk and of memv per (l, img, h).  One thread per (l, img, h, kv, key slot).
@@ -1073,6 +1073,7 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   HM_CHECK(p.fc_tiles % NW == 0 && p.fc_tiles > 0, "decode: bad fc_tiles %d", p.fc_tiles);
   HM_CHECK(p.chunks_per_step == DP_LAYER_CHUNKS * p.num_layers + p.fc_tiles, "decode: bad chunks_per_step");
   HM_CHECK(p.cache_blocks * 32 >= p.tmax, "decode: %d cache blocks cannot hold %d positions", p.cache_blocks, p.tmax);
+  HM_CHECK(p.mem_len >= 1 && p.mem_len <= 32, "decode: %d memory tokens per image (1..32 supported)", p.mem_len);
   HM_CHECK(p.beam >= 1 && p.beam <= DP_MAX_BEAM, "decode: beam %d outside [1, %d]", p.beam, DP_MAX_BEAM);
   const bool beam = p.beam > 1 || p.bm_score != nullptr;     // beam machinery (also runs beam = 1 for the A/B test)
   // Rows per cluster: 8 (greedy) or whole images (beam).  Clusters are independent, so a batch larger than
@@ -1113,11 +1114,12 @@ int beam_finalize(cudaStream_t st, const DecodeState* state, const float* bm_sco
   return 0;
 }
 
-int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, void* memk, void* memv) {
+int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, int mem_len, void* memk, void* memv) {
+  HM_CHECK(mem_len >= 1 && mem_len <= 32, "decode: %d memory tokens per image (1..32 supported)", mem_len);
   const size_t total = (size_t)L * images * NH * 2 * 32;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  repack_memkv_kernel<<<(int)blocks, 256, 0, st>>>(memkv, images, L, static_cast<__half*>(memk), static_cast<__half*>(memv));
+  repack_memkv_kernel<<<(int)blocks, 256, 0, st>>>(memkv, images, L, mem_len, static_cast<__half*>(memk), static_cast<__half*>(memv));
   HM_LAUNCHED();
   return 0;
 }

@@ -36,9 +36,10 @@ struct DecPersistParams {
   // fp16 caches in mma-fragment-major blocks of 32 keys x 32 dims (2048 bytes, layout in decode_persistent.cu)
   __half* kcache;             // [L][rows][8][cache_blocks][1024]
   __half* vcache;             // [L][rows][8][cache_blocks][1024]
-  const __half* memk;         // [L][images][8][1024]   (30 memory tokens, slots 30 and 31 zero)
+  const __half* memk;         // [L][images][8][1024]   (mem_len <= 32 memory tokens, the other slots zero)
   const __half* memv;         // [L][images][8][1024]
   int cache_blocks;           // ceil(max_seq_len / 32)
+  int mem_len;                // memory tokens per image: 30 (Swin-T) or 10 (ResNet-18 variant)
   int64_t* tokens;            // [rows][ld_tok]
   float* logprob;             // [rows][max_len] or nullptr
   uint8_t* finished;          // [rows]
@@ -68,8 +69,8 @@ struct DecPersistParams {
 int decode_persistent_init();
 int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, int t_end);
 int decode_persistent_max_clusters(int* out);   // co-resident clusters on this device
-// memkv f32 [img*30+s][l*512 + kv*256 + h*32 + d] -> the fp16 memk / memv layouts above
-int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, void* memk, void* memv);
+// memkv f32 [img*mem_len+s][l*512 + kv*256 + h*32 + d] -> the fp16 memk / memv layouts above
+int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, int mem_len, void* memk, void* memv);
 constexpr int DP_MAX_BEAM = 5;
 // beam search bookkeeping around the persistent kernel
 int beam_init(cudaStream_t st, DecodeState* state, float* bm_score, int* bm_fin, int* bm_src, int* bm_tok, int rows,

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const int64_t* __restrict__ 
 
 // ---- teacher-forced attention ----------------------------------------------------------------
 __global__ void __launch_bounds__(256) prefill_self_kernel(const h16* __restrict__ qkv, int B, int T,
-                                                           int nhead, h16* __restrict__ ctx) {
+                                                           int nhead, int causal, h16* __restrict__ ctx) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= B * T * nhead) return;
   const int lane = threadIdx.x & 31;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) prefill_self_kernel(const h16* __restrict
   const h16* kb = qkv + (size_t)b * T * pitch + d + h * HD;
   const h16* vb = kb + d;
   const float o = warp_attend(
-      q, t + 1, [&](int j) { return kb + (size_t)j * pitch; }, [&](int j) { return vb + (size_t)j * pitch; }, lane);
+      q, causal ? t + 1 : T, [&](int j) { return kb + (size_t)j * pitch; }, [&](int j) { return vb + (size_t)j * pitch; }, lane);
   ctx[(size_t)(b * T + t) * d + h * HD + lane] = to_h16(o);
 }
 
@@ -279,9 +279,9 @@ int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, 
   return 0;
 }
 
-int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16) {
+int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16, bool causal) {
   HM_CHECK(T <= 32 * MAXK, "attention: T=%d exceeds %d", T, 32 * MAXK);
-  prefill_self_kernel<<<ceil_div(B * T * nhead, 8), 256, 0, st>>>(qkv16, B, T, nhead, ctx16);
+  prefill_self_kernel<<<ceil_div(B * T * nhead, 8), 256, 0, st>>>(qkv16, B, T, nhead, causal ? 1 : 0, ctx16);
   HM_LAUNCHED();
   return 0;
 }

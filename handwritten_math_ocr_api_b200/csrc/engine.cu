@@ -28,7 +28,10 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-constexpr int IMG_H = 96, IMG_W = 320, MEM_S = 30, SWIN_OUT = 768;
+constexpr int IMG_H = 96, IMG_W = 320, SWIN_OUT = 768;
+constexpr int RES18_MEM = 10, SWIN_MEM = 30;
+constexpr int RES18_C[4] = {64, 128, 256, 512};
+constexpr int RES18_STRIDE[4] = {1, 2, 2, 2};
 constexpr int DEPTHS[4] = {2, 2, 6, 2};
 constexpr int HEADS[4] = {3, 6, 12, 24};
 constexpr int STEP_CHUNK = 8;     // decode steps between early-exit polls
@@ -48,6 +51,8 @@ struct Norm { float* g = nullptr; float* b = nullptr; };
 struct SwinBlock { Norm n1, n2; Lin qkv, proj, fc1, fc2; float* rel_bias = nullptr; };
 struct Merge { Norm norm; Lin red; };
 struct DecLayer { Lin sa_in, sa_out, ca_q, ca_out, l1, l2; Norm n1, n2, n3; };
+struct EncLayer { Lin in_proj, out_proj, l1, l2; Norm n1, n2; };        // ResNet variant: nn.TransformerEncoderLayer
+struct ResBlock { Lin conv1, conv2, down; bool has_down = false; };      // BasicBlock, BatchNorm folded
 
 struct Buf {
   void* p = nullptr;
@@ -76,6 +81,14 @@ struct hmocr_engine {
   Lin proj;
   float *emb = nullptr, *pos = nullptr;
   std::vector<DecLayer> layers;
+  // ResNet-18 + TransformerEncoder variant (cfg.encoder_arch == 1)
+  int mem_len = SWIN_MEM;             // memory tokens per image: 30 (Swin-T) / 10 (ResNet-18 variant)
+  float *r18_w1 = nullptr, *r18_b1 = nullptr;     // conv1 7x7 with bn1 folded: [64][49], [64]
+  ResBlock r18_blocks[8];
+  Lin r18_proj;
+  std::vector<EncLayer> enc_layers;
+  float* pos_table = nullptr;         // [10][d] device copy of the positional table given by hmocr_set_pos_table
+  bool pos_table_set = false;
   Lin ca_kv;                          // stacked cross-attention K/V projection of all layers [L*2d, d]
   Lin fc;
   // packed operands of the persistent cluster decode kernel (decode_persistent.cuh)
@@ -196,6 +209,87 @@ int upload_lin(hmocr_engine* e, const std::string& prefix, int n, int k, bool bi
   return upload_lin_rows(e, w->f.data(), b ? b->f.data() : nullptr, n, k, out);
 }
 
+// eval-mode BatchNorm folded into the preceding bias-free convolution: y = conv(x) * g / sqrt(var + eps) + (b - mean * g / sqrt(var + eps))
+int fold_bn(hmocr_engine* e, const std::string& bn, int cout, std::vector<float>* scale, std::vector<float>* shift) {
+  const HostTensor *g, *b, *m, *v;
+  HM_TRY(need(e, bn + ".weight", {cout}, &g));
+  HM_TRY(need(e, bn + ".bias", {cout}, &b));
+  HM_TRY(need(e, bn + ".running_mean", {cout}, &m));
+  HM_TRY(need(e, bn + ".running_var", {cout}, &v));
+  scale->resize(cout); shift->resize(cout);
+  for (int i = 0; i < cout; ++i) {
+    const float sc = g->f[i] / sqrtf(v->f[i] + 1e-5f);
+    (*scale)[i] = sc;
+    (*shift)[i] = b->f[i] - m->f[i] * sc;
+  }
+  return 0;
+}
+
+// conv weight [cout, cin, k, k] (+ folded BN) -> GEMM weight [cout, (ky, kx, cin)] matching im2col's column order
+int upload_conv(hmocr_engine* e, const std::string& conv, const std::string& bn, int cout, int cin, int k, Lin* out) {
+  const HostTensor* w;
+  HM_TRY(need(e, conv + ".weight", {cout, cin, k, k}, &w));
+  std::vector<float> scale, shift;
+  HM_TRY(fold_bn(e, bn, cout, &scale, &shift));
+  std::vector<float> m((size_t)cout * k * k * cin);
+  for (int o = 0; o < cout; ++o)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx)
+          m[(size_t)o * k * k * cin + (size_t)(ky * k + kx) * cin + ci] =
+              w->f[(((size_t)o * cin + ci) * k + ky) * k + kx] * scale[o];
+  return upload_lin_rows(e, m.data(), shift.data(), cout, k * k * cin, out);
+}
+
+int load_res18_weights(hmocr_engine* e) {
+  const hmocr_config& c = e->cfg;
+  const int d = c.d_model, ff = c.dim_feedforward;
+  const std::string f = "encoder.features.";
+  {
+    const HostTensor* w;
+    HM_TRY(need(e, f + "0.weight", {64, 1, 7, 7}, &w));
+    std::vector<float> scale, shift;
+    HM_TRY(fold_bn(e, f + "1", 64, &scale, &shift));
+    std::vector<float> w1(64 * 49);
+    for (int o = 0; o < 64; ++o)
+      for (int i = 0; i < 49; ++i) w1[o * 49 + i] = w->f[o * 49 + i] * scale[o];
+    HM_TRY(upload_f32(e, w1.data(), w1.size(), &e->r18_w1));
+    HM_TRY(upload_f32(e, shift.data(), shift.size(), &e->r18_b1));
+  }
+  int cin = 64;
+  for (int sidx = 0; sidx < 4; ++sidx) {
+    const int cout = RES18_C[sidx];
+    for (int j = 0; j < 2; ++j) {
+      const std::string p = f + std::to_string(4 + sidx) + "." + std::to_string(j) + ".";
+      ResBlock& rb = e->r18_blocks[sidx * 2 + j];
+      HM_TRY(upload_conv(e, p + "conv1", p + "bn1", cout, j == 0 ? cin : cout, 3, &rb.conv1));
+      HM_TRY(upload_conv(e, p + "conv2", p + "bn2", cout, cout, 3, &rb.conv2));
+      rb.has_down = find(e, p + "downsample.0.weight") != nullptr;
+      if (rb.has_down) HM_TRY(upload_conv(e, p + "downsample.0", p + "downsample.1", cout, cin, 1, &rb.down));
+    }
+    cin = cout;
+  }
+  HM_TRY(upload_lin(e, "encoder.projection", d, 512, true, &e->r18_proj));
+  e->enc_layers.resize(c.num_layers);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const std::string p = "encoder.transformer_encoder.layers." + std::to_string(l) + ".";
+    EncLayer& L = e->enc_layers[l];
+    const HostTensor *w, *b;
+    HM_TRY(need(e, p + "self_attn.in_proj_weight", {3 * d, d}, &w));
+    HM_TRY(need(e, p + "self_attn.in_proj_bias", {3 * d}, &b));
+    HM_TRY(upload_lin_rows(e, w->f.data(), b->f.data(), 3 * d, d, &L.in_proj));
+    HM_TRY(upload_lin(e, p + "self_attn.out_proj", d, d, true, &L.out_proj));
+    HM_TRY(upload_lin(e, p + "linear1", ff, d, true, &L.l1));
+    HM_TRY(upload_lin(e, p + "linear2", d, ff, true, &L.l2));
+    HM_TRY(upload_norm(e, p + "norm1", d, &L.n1));
+    HM_TRY(upload_norm(e, p + "norm2", d, &L.n2));
+  }
+  void* pt;
+  HM_TRY(arena_alloc(e, sizeof(float) * RES18_MEM * d, &pt));
+  e->pos_table = static_cast<float*>(pt);
+  return 0;
+}
+
 int run_lin(cudaStream_t st, const h16* a, int lda, int M, const Lin& l, GemmEpilogue epi) {
   epi.bias = l.b;
   return gemm_f16(st, a, lda, M, l.k, l.w, l.n, epi);
@@ -250,7 +344,7 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* 
       H /= 2; W /= 2; C *= 2;
     }
   }
-  const int rows = B * MEM_S;
+  const int rows = B * e->mem_len;
   HM_TRY(f32_to_f16(st, x, (size_t)rows * SWIN_OUT, xn));
   GemmEpilogue eo;
   eo.out_f32 = enc32; eo.ld32 = e->cfg.d_model;
@@ -259,11 +353,104 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ResNet-18 + TransformerEncoder encoder      /root/reference/src/model_res18trans.py:48-64
+// ------------------------------------------------------------------------------------------------
+int conv_gemm(hmocr_engine* e, cudaStream_t st, const h16* x16, int B, int H, int W, int C, int k, int stride,
+              const Lin& w, h16* col, GemmEpilogue epi) {
+  const int pad = (k == 3) ? 1 : 0;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  HM_TRY(im2col(st, x16, B, H, W, C, k, stride, pad, col));
+  return run_lin(st, col, k * k * C, B * Ho * Wo, w, epi);
+}
+
+int encode_res18_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* enc16, cudaStream_t st) {
+  const int d = e->cfg.d_model, ff = e->cfg.dim_feedforward, nh = e->cfg.nhead;
+  HM_CHECK(e->pos_table_set, "ResNet-18 variant: call hmocr_set_pos_table first - the reference draws a fresh "
+                             "nn.Embedding(10, d_model) table on every encoder call (src/model_res18trans.py:57-59)");
+  HM_CHECK(B <= 256, "ResNet-18 variant: the encoder attends ACROSS the batch (SURVEY.md D7); batch %d > 256 unsupported", B);
+  const size_t m1 = (size_t)B * 24 * 80;                       // pixels after the stem
+  h16 *stem, *xa16, *xb16, *h16b, *col;
+  float *xa32, *xb32, *ds32;
+  HM_TRY(ws_get(e, "r18.stem", (size_t)B * 48 * 160 * 64, &stem));
+  HM_TRY(ws_get(e, "r18.xa16", m1 * 64, &xa16));
+  HM_TRY(ws_get(e, "r18.xb16", m1 * 64, &xb16));
+  HM_TRY(ws_get(e, "r18.h16", m1 * 64, &h16b));
+  HM_TRY(ws_get(e, "r18.xa32", m1 * 64, &xa32));
+  HM_TRY(ws_get(e, "r18.xb32", m1 * 64, &xb32));
+  HM_TRY(ws_get(e, "r18.ds32", m1 * 64 / 2, &ds32));
+  HM_TRY(ws_get(e, "r18.col", m1 * 576, &col));
+  HM_TRY(conv7x7_bn_relu(st, images, B, e->r18_w1, e->r18_b1, stem));
+  HM_TRY(maxpool3x3s2(st, stem, B, 48, 160, 64, xa16, xa32));
+  int H = 24, W = 80, C = 64;
+  h16 *x16 = xa16, *y16 = xb16;
+  float *x32 = xa32, *y32 = xb32;
+  for (int sidx = 0; sidx < 4; ++sidx) {
+    for (int j = 0; j < 2; ++j) {
+      const ResBlock& rb = e->r18_blocks[sidx * 2 + j];
+      const int cout = RES18_C[sidx], stride = (j == 0) ? RES18_STRIDE[sidx] : 1;
+      const int Ho = H / stride, Wo = W / stride, M = B * Ho * Wo;
+      GemmEpilogue e1;                                         // relu(bn1(conv1(x)))
+      e1.act = 2; e1.out_f16 = h16b; e1.ld16 = cout;
+      HM_TRY(conv_gemm(e, st, x16, B, H, W, C, 3, stride, rb.conv1, col, e1));
+      const float* identity = x32;
+      if (rb.has_down) {                                       // bn(conv1x1(x)), stride 2
+        GemmEpilogue ed;
+        ed.out_f32 = ds32; ed.ld32 = cout;
+        HM_TRY(conv_gemm(e, st, x16, B, H, W, C, 1, stride, rb.down, col, ed));
+        identity = ds32;
+      }
+      GemmEpilogue e2;                                         // relu(bn2(conv2(.)) + identity)
+      e2.act = 3; e2.residual = identity; e2.ldr = cout; e2.out_f32 = y32; e2.ld32 = cout; e2.out_f16 = y16; e2.ld16 = cout;
+      HM_TRY(conv_gemm(e, st, h16b, B, Ho, Wo, cout, 3, 1, rb.conv2, col, e2));
+      (void)M;
+      h16* t16 = x16; x16 = y16; y16 = t16;
+      float* t32 = x32; x32 = y32; y32 = t32;
+      H = Ho; W = Wo; C = cout;
+    }
+  }
+  // AdaptiveAvgPool2d((1, None)) -> Linear 512 -> d -> + positional table -> [10, B, d] -> 8 encoder layers over B
+  const int S = RES18_MEM, rows = B * S;
+  h16 *pool16, *z16, *qkv, *ctx, *hid;
+  float *q32, *z32;
+  HM_TRY(ws_get(e, "r18.pool16", (size_t)rows * 512, &pool16));
+  HM_TRY(ws_get(e, "r18.q32", (size_t)rows * d, &q32));
+  HM_TRY(ws_get(e, "r18.z32", (size_t)rows * d, &z32));
+  HM_TRY(ws_get(e, "r18.z16", (size_t)rows * d, &z16));
+  HM_TRY(ws_get(e, "r18.qkv", (size_t)rows * 3 * d, &qkv));
+  HM_TRY(ws_get(e, "r18.ctx", (size_t)rows * d, &ctx));
+  HM_TRY(ws_get(e, "r18.hid", (size_t)rows * ff, &hid));
+  HM_TRY(avgpool_h(st, x32, B, H, W, C, pool16));
+  GemmEpilogue ep;
+  ep.out_f32 = q32; ep.ld32 = d;
+  HM_TRY(run_lin(st, pool16, 512, rows, e->r18_proj, ep));
+  HM_TRY(add_pos_permute(st, q32, e->pos_table, B, S, d, z32, z16));
+  for (size_t l = 0; l < e->enc_layers.size(); ++l) {
+    const EncLayer& L = e->enc_layers[l];
+    GemmEpilogue ei;
+    ei.out_f16 = qkv; ei.ld16 = 3 * d;
+    HM_TRY(run_lin(st, z16, d, rows, L.in_proj, ei));
+    HM_TRY(mha_prefill_self(st, qkv, S, B, nh, ctx, /*causal=*/false));      // batch = 10 positions, sequence = B images
+    GemmEpilogue e1;                                                          // x = LN1(x + out_proj(ctx))
+    e1.residual = z32; e1.ldr = d; e1.out_f32 = z32; e1.ld32 = d; e1.out_f16 = z16; e1.ld16 = d;
+    e1.ln_gamma = L.n1.g; e1.ln_beta = L.n1.b;
+    HM_TRY(run_lin(st, ctx, d, rows, L.out_proj, e1));
+    GemmEpilogue ef;
+    ef.act = 2; ef.out_f16 = hid; ef.ld16 = ff;
+    HM_TRY(run_lin(st, z16, d, rows, L.l1, ef));
+    GemmEpilogue e2;                                                          // x = LN2(x + linear2(relu(linear1 x)))
+    e2.residual = z32; e2.ldr = d; e2.out_f32 = z32; e2.ld32 = d; e2.out_f16 = z16; e2.ld16 = d;
+    e2.ln_gamma = L.n2.g; e2.ln_beta = L.n2.b;
+    HM_TRY(run_lin(st, hid, ff, rows, L.l2, e2));
+  }
+  return permute_back(st, z32, B, S, d, enc32, enc16);
+}
+
 // memory K/V of all layers in one GEMM: memkv[b*S+s, l*2d + {0..d-1: K, d..2d-1: V}]
 int project_memory(hmocr_engine* e, const h16* enc16, int B, h16* memkv, cudaStream_t st) {
   GemmEpilogue ek;
   ek.out_f16 = memkv; ek.ld16 = e->ca_kv.n;
-  return run_lin(st, enc16, e->cfg.d_model, B * MEM_S, e->ca_kv, ek);
+  return run_lin(st, enc16, e->cfg.d_model, B * e->mem_len, e->ca_kv, ek);
 }
 
 struct DecBufs {
@@ -297,9 +484,9 @@ int layer_tail(hmocr_engine* e, const DecLayer& L, int l, const DecBufs& b, int 
   eq.out_f16 = b.q; eq.ld16 = d;
   HM_TRY(run_lin(st, b.x16, d, rows, L.ca_q, eq));
   if (T > 0)
-    HM_TRY(mha_prefill_cross(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, rows / T, T, MEM_S, nh, b.ctx));
+    HM_TRY(mha_prefill_cross(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, rows / T, T, e->mem_len, nh, b.ctx));
   else
-    HM_TRY(cross_attn_step(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, mem_row, rows, MEM_S, nh, b.ctx));
+    HM_TRY(cross_attn_step(st, b.q, memkv, e->ca_kv.n, l * 2 * d, l * 2 * d + d, mem_row, rows, e->mem_len, nh, b.ctx));
   GemmEpilogue e2;                       // x = LN2(x + out_proj(ctx))
   e2.residual = b.x32; e2.ldr = d; e2.out_f32 = b.x32; e2.ld32 = d; e2.out_f16 = b.x16; e2.ld16 = d;
   e2.ln_gamma = L.n2.g; e2.ln_beta = L.n2.b;
@@ -322,11 +509,11 @@ int decoder_forward_impl(hmocr_engine* e, const float* enc32, const int64_t* tgt
   const int d = e->cfg.d_model, nh = e->cfg.nhead;
   const int rows = B * T;
   h16 *enc16, *memkv;
-  HM_TRY(ws_get(e, "tf.enc16", (size_t)B * MEM_S * d, &enc16));
-  HM_TRY(ws_get(e, "tf.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  HM_TRY(ws_get(e, "tf.enc16", (size_t)B * e->mem_len * d, &enc16));
+  HM_TRY(ws_get(e, "tf.memkv", (size_t)B * e->mem_len * e->ca_kv.n, &memkv));
   DecBufs b;
   HM_TRY(dec_bufs(e, "tf", rows, &b));
-  HM_TRY(f32_to_f16(st, enc32, (size_t)B * MEM_S * d, enc16));
+  HM_TRY(f32_to_f16(st, enc32, (size_t)B * e->mem_len * d, enc16));
   HM_TRY(project_memory(e, enc16, B, memkv, st));
   HM_TRY(embed_tokens(st, tgt, T, B, T, e->emb, e->pos, d, e->cfg.vocab_size, b.x32, b.x16));
   for (int l = 0; l < e->cfg.num_layers; ++l) {
@@ -390,7 +577,7 @@ int generate_from_memory_impl(hmocr_engine* e, const h16* enc16, int B, int max_
   const int d = e->cfg.d_model, nh = e->cfg.nhead, L = e->cfg.num_layers;
   const int rows = B;
   h16* memkv;
-  HM_TRY(ws_get(e, "gen.memkv", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  HM_TRY(ws_get(e, "gen.memkv", (size_t)B * e->mem_len * e->ca_kv.n, &memkv));
   GenBufs g;
   g.tmax = e->cfg.max_seq_len;
   HM_TRY(dec_bufs(e, "gen", rows, &g.b));
@@ -551,7 +738,7 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   DecodeState* state;
   uint8_t* finished;
   const int tmax = e->cfg.max_seq_len, cache_blocks = (tmax + 31) / 32;
-  HM_TRY(ws_get(e, "dp.memkv32", (size_t)B * MEM_S * e->ca_kv.n, &memkv));
+  HM_TRY(ws_get(e, "dp.memkv32", (size_t)B * e->mem_len * e->ca_kv.n, &memkv));
   HM_TRY(ws_get(e, "dp.memk", (size_t)L * B * nh * 1024, &memk));
   HM_TRY(ws_get(e, "dp.memv", (size_t)L * B * nh * 1024, &memv));
   const size_t set_elems = (size_t)L * rows * nh * cache_blocks * 1024;
@@ -570,9 +757,9 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   {
     GemmEpilogue ek;
     ek.out_f32 = memkv; ek.ld32 = e->ca_kv.n;
-    HM_TRY(run_lin(st, enc16, e->cfg.d_model, B * MEM_S, e->ca_kv, ek));
+    HM_TRY(run_lin(st, enc16, e->cfg.d_model, B * e->mem_len, e->ca_kv, ek));
   }
-  HM_TRY(repack_memkv(st, memkv, B, L, memk, memv));
+  HM_TRY(repack_memkv(st, memkv, B, L, e->mem_len, memk, memv));
   DecPersistParams p;
   memset(&p, 0, sizeof(p));
   p.wstream = e->dp_wstream;
@@ -582,7 +769,7 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   p.rows = rows; p.images = B; p.beam = beam; p.num_layers = L; p.fc_tiles = e->dp_fc_tiles;
   p.chunks_per_step = e->dp_chunks_per_step;
   p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
-  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id; p.pad = e->cfg.pad_id; p.cache_blocks = cache_blocks;
+  p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id; p.pad = e->cfg.pad_id; p.cache_blocks = cache_blocks; p.mem_len = e->mem_len;
   p.trace = nullptr; p.trace_step = e->trace_step; p.flags = e->dbg_flags;
   p.rows_per_cluster = DP_ROWS;
   if (beam_mode) {
@@ -631,10 +818,11 @@ int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int 
                   int32_t* steps, float* score, cudaStream_t st) {
   float* enc32;
   h16* enc16;
-  HM_TRY(ws_get(e, "gen.enc32", (size_t)B * MEM_S * e->cfg.d_model, &enc32));
-  HM_TRY(ws_get(e, "gen.enc16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
+  HM_TRY(ws_get(e, "gen.enc32", (size_t)B * e->mem_len * e->cfg.d_model, &enc32));
+  HM_TRY(ws_get(e, "gen.enc16", (size_t)B * e->mem_len * e->cfg.d_model, &enc16));
   HM_CUDA(cudaEventRecord(e->ev[0], st));
-  HM_TRY(encode_impl(e, images, B, enc32, enc16, st));
+  if (e->cfg.encoder_arch == 1) HM_TRY(encode_res18_impl(e, images, B, enc32, enc16, st));
+  else HM_TRY(encode_impl(e, images, B, enc32, enc16, st));
   HM_CUDA(cudaEventRecord(e->ev[1], st));
   HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));
   HM_CUDA(cudaEventRecord(e->ev[2], st));
@@ -676,6 +864,8 @@ HM_API int hmocr_create(const hmocr_config* cfg, hmocr_engine** out) {
   hmocr_engine* e = new hmocr_engine();
   e->cfg = *cfg;
   HM_CUDA(cudaGetDevice(&e->device));
+  HM_CHECK(cfg->encoder_arch == 0 || cfg->encoder_arch == 1, "encoder_arch must be 0 (Swin-T) or 1 (ResNet-18 + TransformerEncoder)");
+  e->mem_len = cfg->encoder_arch == 1 ? RES18_MEM : SWIN_MEM;
   e->vpad = (cfg->vocab_size + 255) / 256 * 256;
   e->layers.resize(cfg->num_layers);
   HM_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
@@ -714,6 +904,9 @@ HM_API int hmocr_load_weight(hmocr_engine* e, const char* key, const void* data,
   // share storage, src/model_swin.py:35); keep one canonical name
   const std::string alias = "encoder.swin.features.";
   if (k.compare(0, alias.size(), alias) == 0) k = "encoder.features." + k.substr(alias.size());
+  // src/model_res18trans.py names the same decoder module `transformer_decoder`
+  const std::string dec2 = "decoder.transformer_decoder.";
+  if (k.compare(0, dec2.size(), dec2) == 0) k = "decoder.decoder." + k.substr(dec2.size());
   HostTensor t;
   size_t n = 1;
   for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
@@ -738,6 +931,9 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
 
   const std::string f = "encoder.features.";
   const HostTensor* t;
+  if (c.encoder_arch == 1) {
+    HM_TRY(load_res18_weights(e));
+  } else {
   HM_TRY(need(e, f + "0.0.weight", {96, 1, 4, 4}, &t));
   HM_TRY(upload_f32(e, t->f.data(), 96 * 16, &e->pe_w));
   HM_TRY(upload_vec(e, f + "0.0.bias", 96, &e->pe_b));
@@ -775,6 +971,7 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
     }
   }
   HM_TRY(upload_lin(e, "encoder.projection", d, SWIN_OUT, true, &e->proj));
+  }
 
   HM_TRY(need(e, "decoder.embedding.weight", {V, d}, &t));
   HM_TRY(upload_f32(e, t->f.data(), (size_t)V * d, &e->emb));
@@ -818,6 +1015,16 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   return 0;
 }
 
+HM_API int hmocr_set_pos_table(hmocr_engine* e, const float* pos_host, int rows, int d) {
+  HM_CHECK(e != nullptr && pos_host != nullptr, "hmocr_set_pos_table: null argument");
+  HM_CHECK(e->finalized && e->cfg.encoder_arch == 1, "hmocr_set_pos_table: only for a loaded ResNet-18 variant engine");
+  HM_CHECK(rows == RES18_MEM && d == e->cfg.d_model, "positional table must be [%d, %d]", RES18_MEM, e->cfg.d_model);
+  HM_CUDA(cudaSetDevice(e->device));
+  HM_CUDA(cudaMemcpy(e->pos_table, pos_host, sizeof(float) * rows * d, cudaMemcpyHostToDevice));
+  e->pos_table_set = true;
+  return 0;
+}
+
 HM_API int hmocr_decode_max_clusters(int* out) {
   HM_CHECK(out != nullptr, "null argument");
   return decode_persistent_max_clusters(out);
@@ -858,8 +1065,9 @@ HM_API int hmocr_encode(hmocr_engine* e, const float* images, int B, float* enc_
   HM_TRY(check_ready(e, B));
   HM_CHECK(images != nullptr && enc_out != nullptr, "hmocr_encode: null buffer");
   h16* enc16;
-  HM_TRY(ws_get(e, "enc.out16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
-  return encode_impl(e, images, B, enc_out, enc16, static_cast<cudaStream_t>(stream));
+  HM_TRY(ws_get(e, "enc.out16", (size_t)B * e->mem_len * e->cfg.d_model, &enc16));
+  return e->cfg.encoder_arch == 1 ? encode_res18_impl(e, images, B, enc_out, enc16, static_cast<cudaStream_t>(stream))
+                                  : encode_impl(e, images, B, enc_out, enc16, static_cast<cudaStream_t>(stream));
 }
 
 HM_API int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out, const int64_t* tgt, int B, int T,
@@ -884,8 +1092,8 @@ HM_API int hmocr_generate_from_memory(hmocr_engine* e, const float* enc_out, int
   HM_CHECK(enc_out != nullptr && tokens != nullptr, "hmocr_generate_from_memory: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   h16* enc16;
-  HM_TRY(ws_get(e, "gen.enc16", (size_t)B * MEM_S * e->cfg.d_model, &enc16));
-  HM_TRY(f32_to_f16(st, enc_out, (size_t)B * MEM_S * e->cfg.d_model, enc16));
+  HM_TRY(ws_get(e, "gen.enc16", (size_t)B * e->mem_len * e->cfg.d_model, &enc16));
+  HM_TRY(f32_to_f16(st, enc_out, (size_t)B * e->mem_len * e->cfg.d_model, enc16));
   HM_CUDA(cudaEventRecord(e->ev[0], st));
   HM_CUDA(cudaEventRecord(e->ev[1], st));
   HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));

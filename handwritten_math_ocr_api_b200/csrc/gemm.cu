@@ -124,6 +124,7 @@ __device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t t
       if (e.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
       else if (e.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+      if (e.act == 3) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (row < M && !((dbg & 1) && v.x != 12345.678f)) {
         if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld32 + col) = v;
         if (e.out_f16 != nullptr)

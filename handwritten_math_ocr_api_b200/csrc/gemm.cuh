@@ -6,7 +6,7 @@ namespace hmocr {
 
 struct GemmEpilogue {
   const float* bias = nullptr;        // [N] fp32
-  int act = 0;                        // 0 none, 1 GELU(erf), 2 ReLU
+  int act = 0;                   // 0 none, 1 GELU(erf), 2 ReLU, 3 ReLU applied AFTER the residual add (ResNet BasicBlock)
   const float* residual = nullptr;    // fp32 [M, ldr]; may alias out_f32 (in-place residual add)
   int ldr = 0;
   float* out_f32 = nullptr;           // fp32 [M, ld32]

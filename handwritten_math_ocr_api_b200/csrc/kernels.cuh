@@ -31,7 +31,7 @@ int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, 
 // teacher-forced attention over a [B*T, ...] activation buffer: one warp per (b, head, query)
 //   self : q,k,v = columns [0,d),[d,2d),[2d,3d) of qkv16 (row pitch 3d), causal
 //   cross: q from q16 (pitch d); k,v from memkv (row (b*S+s), pitch ld_mem, column offsets koff/voff)
-int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16);
+int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16, bool causal = true);
 int mha_prefill_cross(cudaStream_t st, const h16* q16, const h16* memkv, int ld_mem, int koff,
                       int voff, int B, int T, int S, int nhead, h16* ctx16);
 
@@ -54,6 +54,14 @@ int init_decode(cudaStream_t st, DecodeState* state, int64_t* tokens, int ld_tok
 // after the loop: columns past steps_executed -> pad / 0, steps -> int32 out
 int finalize_decode(cudaStream_t st, const DecodeState* state, int64_t* tokens, int ld_tok, int rows, int max_len,
                     int pad, float* logprob, int32_t* steps_out);
+
+// ---- ResNet-18 + TransformerEncoder encoder (resnet_kernels.cu; BASELINE.json config 4) ----------------------
+int conv7x7_bn_relu(cudaStream_t st, const float* images, int B, const float* w, const float* bias, h16* out);
+int maxpool3x3s2(cudaStream_t st, const h16* in, int B, int H, int W, int C, h16* out16, float* out32);
+int im2col(cudaStream_t st, const h16* in, int B, int H, int W, int C, int k, int stride, int pad, h16* out);
+int avgpool_h(cudaStream_t st, const float* in, int B, int H, int W, int C, h16* out);
+int add_pos_permute(cudaStream_t st, const float* x, const float* pos, int B, int S, int d, float* o32, h16* o16);
+int permute_back(cudaStream_t st, const float* x, int B, int S, int d, float* o32, h16* o16);
 
 // misc
 int copy_logits(cudaStream_t st, const float* src, int ld, int rows, int n_valid, float* dst);

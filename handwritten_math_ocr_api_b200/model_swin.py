@@ -67,12 +67,7 @@ class EncoderSwin:
         return self.forward(x)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        m = self._m
-        x = m._images(x)
-        out = torch.empty(x.shape[0], MEM_TOKENS, m.d_model, dtype=torch.float32, device=m.device)
-        with torch.cuda.device(m.device):
-            _lib.check(m._eng.lib.hmocr_encode(m._handle(), _ptr(x), x.shape[0], _ptr(out), _stream()), "hmocr_encode")
-        return out
+        return self._m._encoder_call(x)
 
 
 class DecoderTransformer:
@@ -88,8 +83,8 @@ class DecoderTransformer:
         m = self._m
         enc = encoder_out.to(device=m.device, dtype=torch.float32).contiguous()
         tgt = tgt.to(device=m.device, dtype=torch.int64).contiguous()
-        if enc.dim() != 3 or enc.shape[1] != MEM_TOKENS or enc.shape[2] != m.d_model:
-            raise ValueError(f"encoder_out must be [B,{MEM_TOKENS},{m.d_model}], got {tuple(enc.shape)}")
+        if enc.dim() != 3 or enc.shape[1] != m.mem_tokens or enc.shape[2] != m.d_model:
+            raise ValueError(f"encoder_out must be [B,{m.mem_tokens},{m.d_model}], got {tuple(enc.shape)}")
         if tgt.dim() != 2 or tgt.shape[0] != enc.shape[0]:
             raise ValueError(f"tgt must be [B,T] with B={enc.shape[0]}, got {tuple(tgt.shape)}")
         B, T = tgt.shape
@@ -114,6 +109,10 @@ class FormulaRecognitionModel:
     flavour (``src/model_swin.py:100``: ``captions[:, :-1]``).
     """
 
+    ENCODER_ARCH = 0          # hmocr_config.encoder_arch: 0 = Swin-T
+    MEM_TOKENS = MEM_TOKENS   # memory tokens per image the encoder produces
+    DECODER_LAYERS_ATTR = ("swin_num_decoder_layers", "num_decoder_layers")
+
     def __init__(self, vocab_size: int, config=None, device=None, drop_last_caption: bool = False,
                  sos_id: int = 1, eos_id: int = 2, pad_id: int = 0):
         cfg = config if config is not None else _default_config
@@ -127,11 +126,16 @@ class FormulaRecognitionModel:
         self.vocab_size = int(vocab_size)
         self.d_model = int(cfg.d_model)
         self.max_seq_len = int(cfg.max_seq_len)
-        self.num_layers = int(getattr(cfg, "swin_num_decoder_layers", getattr(cfg, "num_decoder_layers", 8)))
+        self.mem_tokens = self.MEM_TOKENS
+        self.num_layers = 8
+        for attr in self.DECODER_LAYERS_ATTR:
+            if hasattr(cfg, attr):
+                self.num_layers = int(getattr(cfg, attr))
+                break
         self.drop_last_caption = drop_last_caption
         self.sos_id, self.eos_id, self.pad_id = sos_id, eos_id, pad_id
         c = _lib.HmocrConfig(self.vocab_size, self.d_model, int(cfg.nhead), int(cfg.dim_feedforward), self.num_layers,
-                             self.max_seq_len, sos_id, eos_id, pad_id)
+                             self.max_seq_len, sos_id, eos_id, pad_id, self.ENCODER_ARCH)
         self._eng = _Engine(c, self.device)
         self._n_params = 0
         self.encoder = EncoderSwin(self)
@@ -186,7 +190,7 @@ class FormulaRecognitionModel:
                     dt = 1
                 else:
                     t, dt = t.to(torch.float32), 0
-                    if not k.startswith("encoder.features.") and k != "decoder.tgt_mask":
+                    if self._counts_as_parameter(k):
                         n_params += t.numel()
                 t = t.contiguous()
                 keep.append(t)
@@ -197,6 +201,11 @@ class FormulaRecognitionModel:
         self._n_params = n_params
         self._eng.loaded = True
         return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    @staticmethod
+    def _counts_as_parameter(key: str) -> bool:
+        # encoder.features.* aliases encoder.swin.features.* (same storage); tgt_mask is a buffer
+        return not key.startswith("encoder.features.") and key != "decoder.tgt_mask"
 
     @classmethod
     def from_reference(cls, module, config=None, device=None, **kw) -> "FormulaRecognitionModel":
@@ -209,6 +218,13 @@ class FormulaRecognitionModel:
         return m
 
     # ---- forward ------------------------------------------------------------------------------------
+    def _encoder_call(self, x: torch.Tensor) -> torch.Tensor:
+        x = self._images(x)
+        out = torch.empty(x.shape[0], self.mem_tokens, self.d_model, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._eng.lib.hmocr_encode(self._handle(), _ptr(x), x.shape[0], _ptr(out), _stream()), "hmocr_encode")
+        return out
+
     def _images(self, x: torch.Tensor) -> torch.Tensor:
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, IMG_H, IMG_W):

@@ -38,6 +38,8 @@ typedef struct hmocr_config {
   int32_t num_layers;      /* config.swin_num_decoder_layers / num_decoder_layers = 8          */
   int32_t max_seq_len;     /* config.max_seq_len      = 150 (size of pos_encoder / tgt_mask)   */
   int32_t sos_id, eos_id, pad_id; /* vocab['<sos>'], vocab['<eos>'], vocab['<pad>'] = 1, 2, 0  */
+  int32_t encoder_arch;    /* 0 = Swin-T (src/model_swin.py, 30 memory tokens);
+                              1 = ResNet-18 + TransformerEncoder (src/model_res18trans.py, 10 memory tokens) */
 } hmocr_config;
 
 enum { HMOCR_F32 = 0, HMOCR_I64 = 1 };
@@ -70,6 +72,11 @@ int hmocr_set_option(hmocr_engine* e, const char* name, int value);
  * of (cluster 0, CTA 0, thread 0) at every phase boundary of decode step t; this copies the first
  * n (<= 1024) stamps to the host (profiles/ phase breakdowns come from here). */
 int hmocr_read_trace(hmocr_engine* e, int64_t* out_host, int n);
+
+/* ResNet-18 variant only: the positional table added to the 10 pooled tokens.  The reference creates a fresh
+ * N(0,1)-initialised nn.Embedding(10, d_model) on EVERY encoder call (src/model_res18trans.py:57-59), so the
+ * table is an input here: pos_host f32 [10, d_model].  Used by the following hmocr_encode / hmocr_generate calls. */
+int hmocr_set_pos_table(hmocr_engine* e, const float* pos_host, int rows, int d);
 
 /* How many 8-CTA decode clusters (16 sequences each) can be co-resident on the current device. */
 int hmocr_decode_max_clusters(int* out);
