@@ -288,7 +288,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
         sc[4 * b + 2 * tile] = (key < n) ? c[0] : -INFINITY;
         sc[4 * b + 2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
       }
-      if (COPY) store_block(reinterpret_cast<uint4*>(Kd) + lane, b, d);
+      if (COPY && Kd != nullptr) store_block(reinterpret_cast<uint4*>(Kd) + lane, b, d);
       if (b + 4 < NB && b + 4 < nb) load_block(Kl, b + 4, d);       // next K block of this slot ...
       else load_block(Vl, b & 3, d);                                // ... or its first V block (b & 3 < nb here)
     } else {
@@ -329,7 +329,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
       mma_f16(acc1, d[1].x, d[1].y, d[1].z, d[1].w, p0.x, p0.y);
       mma_f16(acc0, d[2].x, d[2].y, d[2].z, d[2].w, p1.x, p1.y);
       mma_f16(acc1, d[3].x, d[3].y, d[3].z, d[3].w, p1.x, p1.y);
-      if (COPY) store_block(reinterpret_cast<uint4*>(Vd) + lane, b, d);
+      if (COPY && Vd != nullptr) store_block(reinterpret_cast<uint4*>(Vd) + lane, b, d);
       if (b + 4 < NB && b + 4 < nb) load_block(Vl, b + 4, d);
     }
   }
@@ -654,7 +654,8 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         float o[4];
         long long* tr = (tracing && t == p.trace_step && ti + 3 < 1024) ? p.trace + ti : nullptr;
         attend_mma<NB, true, BEAM>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0],
-                                   lane, kv, o, tr, Kd, Vd);
+                                   lane, kv, o, tr, row_ok ? Kd : nullptr, row_ok ? Vd : nullptr);   // padding warps
+        // recompute the last valid row: they must not copy its blocks (a late copy would overwrite the append below)
         if (tr) ti += 3;
         send_ctx(o);
         if (BEAM) __syncwarp();                                // the block copies above are ordered before the append

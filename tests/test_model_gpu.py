@@ -369,3 +369,22 @@ def test_beam_search_is_batch_invariant(model, golden_src):
         one, s1, _, sc = model.generate(encoder_out=feats[i:i + 1], beam_size=5, max_len=30)
         n = min(one.shape[1], all_tok.shape[1])
         assert torch.equal(one[0, :n], all_tok[i, :n]) and abs(float(sc[0]) - float(all_score[i])) < 1e-5
+
+
+@pytest.mark.parametrize("beam", [1, 5])
+def test_decode_is_bitwise_repeatable(model, beam):
+    """The exchanges between the 8 CTAs of a cluster are hand-rolled (st.async + mbarrier, shared slots, named
+    barriers): a race would show up as run-to-run differences.  Every cluster computes the same thing on every
+    run, so tokens AND log-probabilities / scores must be bit-identical across repetitions, for a batch that mixes
+    full and partial clusters and co-resident CTAs."""
+    from oracle.synth import synth_images
+    imgs = synth_images(8, seed=99).cuda().repeat(6, 1, 1, 1)[:45].contiguous()
+    feats = model.encoder(imgs)
+    ref = None
+    for _ in range(6):
+        out = model.generate(encoder_out=feats, max_len=70, beam_size=beam, return_logprobs=(beam == 1))
+        cur = (out[0].clone(), out[2].clone() if beam == 1 else out[3].clone())
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])
