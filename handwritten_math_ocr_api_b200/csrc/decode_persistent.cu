@@ -972,32 +972,43 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   cluster_sync_all();      // no CTA exits while a peer may still address its shared memory
 }
 
-__global__ void repack_memkv_kernel(const float* __restrict__ memkv, int images, int L, int MEM_S,
-                                    __half* __restrict__ memk, __half* __restrict__ memv) {
-  // memkv f32 [img*30+s][l*512 + kv*256 + h*32 + d]  ->  one fragment-major block (32 key slots, keys 30 and 31
-  // zero) of memk and of memv per (l, img, h).  One thread per (l, img, h, kv, key slot).
-  const size_t total = (size_t)L * images * NH * 2 * 32;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int key = i & 31, kv = (i >> 5) & 1, h = (i >> 6) & 7;
-    const size_t rest = i >> 9;
+// memkv f32 [img*mem_len+s][l*512 + kv*256 + h*32 + d]  ->  one fragment-major block (32 key slots, the slots past
+// mem_len zero) of memk and of memv per (l, img, h).  One warp per (l, img, h, kv): lane = key slot; the block is
+// assembled in shared memory (fragment order) and written out as 2 KB of coalesced 16-byte stores.
+__global__ void __launch_bounds__(256) repack_memkv_kernel(const float* __restrict__ memkv, int images, int L, int MEM_S,
+                                                           __half* __restrict__ memk, __half* __restrict__ memv) {
+  __shared__ __align__(16) __half tile[8][1024];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const size_t total = (size_t)L * images * NH * 2;
+  for (size_t item = blockIdx.x * 8 + wib; item < total; item += (size_t)gridDim.x * 8) {
+    const int kv = item & 1, h = (item >> 1) & 7;
+    const size_t rest = item >> 4;
     const size_t img = rest % images;
     const int l = (int)(rest / images);
-    const size_t blk = (((size_t)l * images + img) * NH + h) * 1024;
-    const float* src = memkv + (img * MEM_S + min(key, MEM_S - 1)) * (size_t)L * 512 + l * 512 + kv * 256 + h * 32;
+    const int key = lane;
     const bool ok = key < MEM_S;
-    if (kv == 0) {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(memk + blk);
-#pragma unroll 4
-      for (int w = 0; w < 16; ++w) {
-        const __half2 v = ok ? __halves2half2(to_half_sat(src[2 * w]), to_half_sat(src[2 * w + 1]))
-                             : __floats2half2_rn(0.f, 0.f);
-        dst[kfrag_word(key, w)] = *reinterpret_cast<const uint32_t*>(&v);
-      }
-    } else {
-#pragma unroll 4
-      for (int d = 0; d < HD; ++d)
-        memv[blk + vfrag_half(key, d)] = ok ? to_half_sat(src[d]) : __float2half(0.f);
+    const float* src = memkv + (img * MEM_S + min(key, MEM_S - 1)) * (size_t)L * 512 + l * 512 + kv * 256 + h * 32;
+    float v[HD];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
+    __half* t = tile[wib];
+    if (kv == 0) {
+      uint32_t* tw = reinterpret_cast<uint32_t*>(t);
+#pragma unroll
+      for (int w = 0; w < 16; ++w) tw[kfrag_word(key, w)] = pack16(v[2 * w], v[2 * w + 1]);
+    } else {
+#pragma unroll
+      for (int d = 0; d < HD; ++d) t[vfrag_half(key, d)] = to_h16(v[d]);
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>((kv ? memv : memk) + ((((size_t)l * images + img) * NH + h) << 10));
+    const uint4* s4 = reinterpret_cast<const uint4*>(t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q * 32 + lane] = s4[q * 32 + lane];
+    __syncwarp();
   }
 }
 
@@ -1117,8 +1128,8 @@ int beam_finalize(cudaStream_t st, const DecodeState* state, const float* bm_sco
 
 int repack_memkv(cudaStream_t st, const float* memkv, int images, int L, int mem_len, void* memk, void* memv) {
   HM_CHECK(mem_len >= 1 && mem_len <= 32, "decode: %d memory tokens per image (1..32 supported)", mem_len);
-  const size_t total = (size_t)L * images * NH * 2 * 32;
-  size_t blocks = (total + 255) / 256;
+  const size_t total = (size_t)L * images * NH * 2;          // one warp per (l, image, head, K|V)
+  size_t blocks = (total + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   repack_memkv_kernel<<<(int)blocks, 256, 0, st>>>(memkv, images, L, mem_len, static_cast<__half*>(memk), static_cast<__half*>(memv));
   HM_LAUNCHED();

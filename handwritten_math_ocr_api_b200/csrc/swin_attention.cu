@@ -50,6 +50,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -70,7 +75,10 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
   const int nww = Wp / WS, nwin = (Hp / WS) * nww;
   const int total = B * nwin;
   const bool masked = (sh + sw) > 0;
-  const float scale = 0.17677669529663687f;                  // 32^-0.5 (swin_transformer.py:188)
+  // softmax on ex2: log2(e) is folded into the q scale (32^-0.5, swin_transformer.py:188), the bias table and the mask
+  const float LOG2E = 1.4426950408889634f;
+  const float scale = 0.17677669529663687f * LOG2E;
+  const float mask_val = -100.0f * LOG2E;
 
   // one-time: zero the padding rows (finite operands for the masked / zero-probability lanes) and
   // fetch this head's relative-position bias
@@ -79,7 +87,8 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
     (&s.v[WN][0])[i] = to_h16(0.f);
     (&s.q[WN][0])[i] = to_h16(0.f);
   }
-  for (int i = lane; i < WN * WN; i += 32) s.bias[i / WN][i % WN] = __ldg(rel_bias + (size_t)h * WN * WN + i);
+  for (int i = lane; i < WN * WN; i += 32) s.bias[i / WN][i % WN] = __ldg(rel_bias + (size_t)h * WN * WN + i) * LOG2E;
+  for (int i = lane; i < WN; i += 32) s.bias[i][WN] = 0.f;     // column 49 is read (and discarded) by the float2 loads
   __syncwarp();
 
   for (int wi = gw / heads; wi < total; wi += per_head) {
@@ -99,6 +108,12 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
       s.region[p] = reg;
     }
     __syncwarp();
+    // most windows lie in ONE region of the shift mask (only the last window row / column is cut): warp-uniform test
+    bool mixed = false;
+    if (masked) {
+      const int r0 = s.region[0];
+      mixed = __any_sync(0xffffffffu, s.region[lane] != r0 || s.region[min(lane + 32, WN - 1)] != r0);
+    }
     for (int i = lane; i < WN * 12; i += 32) {
       const int p = i / 12, m = (i % 12) >> 2, ch = i & 3;
       h16* dst = (m == 0 ? &s.q[p][0] : (m == 1 ? &s.k[p][0] : &s.v[p][0])) + ch * 8;
@@ -134,19 +149,22 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
         mma16816(c, aq[0], bk);
         ldsm2(smem_u32(&s.k[nt * 8 + (lane & 7)][((lane >> 3) & 1) * 8 + 16]), bk);
         mma16816(c, aq[1], bk);
-        const int c0 = nt * 8 + 2 * t4;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = c0 + e;
-          float v0 = -INFINITY, v1 = -INFINITY;
-          if (col < WN) {
-            const int regc = s.region[col];
-            v0 = c[e] * scale + s.bias[rb0][col] + ((masked && regc != reg0) ? -100.0f : 0.0f);
-            v1 = c[2 + e] * scale + s.bias[rb1][col] + ((masked && regc != reg1) ? -100.0f : 0.0f);
-          }
-          sc[nt][e] = v0; sc[nt][2 + e] = v1;
-          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+        const int c0 = nt * 8 + 2 * t4;                      // columns c0, c0 + 1 (c0 is even, <= 54)
+        const float2 b0 = *reinterpret_cast<const float2*>(&s.bias[rb0][min(c0, WN - 1) & ~1]);
+        const float2 b1 = *reinterpret_cast<const float2*>(&s.bias[rb1][min(c0, WN - 1) & ~1]);
+        float v[4] = {fmaf(c[0], scale, b0.x), fmaf(c[1], scale, b0.y), fmaf(c[2], scale, b1.x), fmaf(c[3], scale, b1.y)};
+        if (mixed) {
+          const int rc0 = s.region[min(c0, WN - 1)], rc1 = s.region[min(c0 + 1, WN - 1)];
+          if (rc0 != reg0) v[0] += mask_val;
+          if (rc1 != reg0) v[1] += mask_val;
+          if (rc0 != reg1) v[2] += mask_val;
+          if (rc1 != reg1) v[3] += mask_val;
         }
+        if (c0 >= WN) { v[0] = -INFINITY; v[2] = -INFINITY; }
+        if (c0 + 1 >= WN) { v[1] = -INFINITY; v[3] = -INFINITY; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[nt][e] = v[e];
+        mx0 = fmaxf(mx0, fmaxf(v[0], v[1])); mx1 = fmaxf(mx1, fmaxf(v[2], v[3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
@@ -154,8 +172,8 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
       uint32_t pa[4][4];
 #pragma unroll
       for (int nt = 0; nt < 7; ++nt) {
-        const float p0 = __expf(sc[nt][0] - mx0), p1 = __expf(sc[nt][1] - mx0);
-        const float p2 = __expf(sc[nt][2] - mx1), p3 = __expf(sc[nt][3] - mx1);
+        const float p0 = ex2_approx(sc[nt][0] - mx0), p1 = ex2_approx(sc[nt][1] - mx0);
+        const float p2 = ex2_approx(sc[nt][2] - mx1), p3 = ex2_approx(sc[nt][3] - mx1);
         sum0 += p0 + p1; sum1 += p2 + p3;
         pa[nt >> 1][(nt & 1) * 2] = pack16(p0, p1);        // row g4   , keys nt*8 + 2*t4 ..
         pa[nt >> 1][(nt & 1) * 2 + 1] = pack16(p2, p3);    // row g4+8
