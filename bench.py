@@ -168,7 +168,8 @@ def run_ours(args, rank, local_rank, world):
     from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib
     from handwritten_math_ocr_api_b200.parallel import gather_tokens, gather_tokens_device
     from handwritten_math_ocr_api_b200.layout import ModelConfig
-    from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict
+    from handwritten_math_ocr_api_b200.preprocess import preprocess_u8
+    from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_images_u8, synth_state_dict
 
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
@@ -179,7 +180,8 @@ def run_ours(args, rank, local_rank, world):
     sd = synth_state_dict(cfg, seed=0, eos_bias_sigma=0.0)     # never emits eos: exactly B*T tokens per step
     model = FormulaRecognitionModel(cfg.vocab_size, device=dev)
     model.load_state_dict(sd)
-    host_imgs = synth_images(B, seed=1234 + rank).pin_memory()
+    host_u8 = synth_images_u8(B, seed=1234 + rank).pin_memory()      # the rendered strokes as they come: uint8 96x320
+    host_imgs = synth_images(B, seed=1234 + rank)                    # = ToTensor + Normalize(0.5, 0.5) of host_u8
     dev_imgs = host_imgs.to(dev)
     lib = _lib.load()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
@@ -236,12 +238,13 @@ def run_ours(args, rank, local_rank, world):
 
     def step_e2e():
         if world == 1:
-            _lib.check(lib.hmocr_generate_host(model._handle(), C.c_void_p(host_imgs.data_ptr()), B, T, 1,
-                                               C.c_void_p(tok_host.data_ptr()), None, C.c_void_p(steps_host.data_ptr()),
-                                               None, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "generate_host")
+            _lib.check(lib.hmocr_generate_host_u8(model._handle(), C.c_void_p(host_u8.data_ptr()), B, T, 1,
+                                                  C.c_void_p(tok_host.data_ptr()), None, C.c_void_p(steps_host.data_ptr()),
+                                                  None, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "generate_host_u8")
             return
         # host images in, gathered ids of the whole job out (every rank reads them), all stream-ordered
-        x = host_imgs.to(dev, non_blocking=True)
+        x = preprocess_u8(model, host_u8.to(dev, non_blocking=True))
         tok, st, _ = model.generate_device(x, max_len=T)
         all_tok, all_steps = gather_tokens_device(tok, st)
         all_host.copy_(all_tok, non_blocking=True)
@@ -300,7 +303,9 @@ def run_ours(args, rank, local_rank, world):
                                      "unit": "TFLOP/s", "frac": enc_tf / pk["bf16_tflops_sustained"],
                                      "gflop_per_image": ENC_GFLOP_PER_IMAGE,
                                      "gflop_per_image_minimal": ENC_GFLOP_MINIMAL}},
-            "e2e": {"value": total_imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * 96 * 320 * 4,
+            "e2e": {"value": total_imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * 96 * 320,
+                    "input": "pinned uint8 [B,96,320] rendered strokes; ToTensor + Normalize(0.5,0.5) on the device "
+                             "(hmocr_generate_host_u8), token ids back to pinned host memory",
                     "d2h_bytes_per_step": (B if world == 1 else world * B) * (T + 1) * 8 + 4},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -1128,6 +1128,41 @@ HM_API int hmocr_generate_host(hmocr_engine* e, const float* images_host, int B,
   return 0;
 }
 
+HM_API int hmocr_preprocess_u8(hmocr_engine* e, const uint8_t* images_u8_dev, int B, float* images_dev, void* stream) {
+  HM_CHECK(e != nullptr && images_u8_dev != nullptr && images_dev != nullptr && B >= 1, "hmocr_preprocess_u8: bad argument");
+  HM_CUDA(cudaSetDevice(e->device));
+  return preprocess_u8(static_cast<cudaStream_t>(stream), images_u8_dev, (size_t)B * IMG_H * IMG_W, images_dev);
+}
+
+HM_API int hmocr_generate_host_u8(hmocr_engine* e, const uint8_t* images_u8_host, int B, int max_len, int beam,
+                                  int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
+                                  void* stream) {
+  HM_TRY(check_ready(e, B));
+  HM_CHECK(images_u8_host != nullptr && tokens_host != nullptr, "hmocr_generate_host_u8: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* u8_d;
+  float *img_d, *lp_d, *score_d;
+  int64_t* tok_d;
+  int32_t* steps_d;
+  const size_t img_n = (size_t)B * IMG_H * IMG_W;
+  HM_TRY(ws_get(e, "host.images_u8", img_n, &u8_d));
+  HM_TRY(ws_get(e, "host.images", img_n, &img_d));
+  HM_TRY(ws_get(e, "host.tokens", (size_t)B * (max_len + 1), &tok_d));
+  HM_TRY(ws_get(e, "host.logprob", (size_t)B * max_len, &lp_d));
+  HM_TRY(ws_get(e, "host.steps", 1, &steps_d));
+  HM_TRY(ws_get(e, "host.score", B, &score_d));
+  HM_CUDA(cudaMemcpyAsync(u8_d, images_u8_host, img_n, cudaMemcpyHostToDevice, st));
+  HM_TRY(preprocess_u8(st, u8_d, img_n, img_d));
+  HM_TRY(generate_impl(e, img_d, B, max_len, beam, tok_d, logprob_host ? lp_d : nullptr, steps_d,
+                       score_host ? score_d : nullptr, st));
+  HM_CUDA(cudaMemcpyAsync(tokens_host, tok_d, sizeof(int64_t) * B * (max_len + 1), cudaMemcpyDeviceToHost, st));
+  if (logprob_host) HM_CUDA(cudaMemcpyAsync(logprob_host, lp_d, sizeof(float) * B * max_len, cudaMemcpyDeviceToHost, st));
+  if (steps_host) HM_CUDA(cudaMemcpyAsync(steps_host, steps_d, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (score_host) HM_CUDA(cudaMemcpyAsync(score_host, score_d, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  HM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 HM_API int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_ms) {
   HM_CHECK(e != nullptr, "null engine");
   if (e->timings_pending) {

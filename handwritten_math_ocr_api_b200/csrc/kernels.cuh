@@ -63,6 +63,9 @@ int avgpool_h(cudaStream_t st, const float* in, int B, int H, int W, int C, h16*
 int add_pos_permute(cudaStream_t st, const float* x, const float* pos, int B, int S, int d, float* o32, h16* o16);
 int permute_back(cudaStream_t st, const float* x, int B, int S, int d, float* o32, h16* o16);
 
+// uint8 grayscale 96x320 images -> normalised f32 (ToTensor + Normalize(0.5, 0.5)), bit-identical to torchvision
+int preprocess_u8(cudaStream_t st, const uint8_t* in, size_t pixels, float* out);
+
 // misc
 int copy_logits(cudaStream_t st, const float* src, int ld, int rows, int n_valid, float* dst);
 int f32_to_f16(cudaStream_t st, const float* src, size_t n, h16* dst);

@@ -148,6 +148,25 @@ __global__ void __launch_bounds__(256) permute_back_kernel(const float* __restri
   }
 }
 
+// ToTensor + Normalize(0.5, 0.5) of app/src/preprocess.py:7-12 / src/predict.py:36-41 on the device:
+// uint8 [B,96,320] (grayscale, already 96 x 320) -> f32 [B,1,96,320] = (u / 255 - 0.5) / 0.5, same operation order
+// and IEEE divisions as torchvision, so the result is bit-identical to the host transform.  16 pixels per thread.
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ in, size_t n16, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float4* o = reinterpret_cast<float4*>(out) + i * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        v[b] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((w[q] >> (8 * b)) & 0xffu), 255.0f), 0.5f), 0.5f);
+      o[q] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
 int blocks_for(size_t total) {
   size_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
@@ -156,6 +175,12 @@ int blocks_for(size_t total) {
 
 }  // namespace
 
+int preprocess_u8(cudaStream_t st, const uint8_t* in, size_t pixels, float* out) {
+  HM_CHECK(pixels % 16 == 0, "preprocess: pixel count must be a multiple of 16");
+  preprocess_u8_kernel<<<blocks_for(pixels / 16), 256, 0, st>>>(in, pixels / 16, out);
+  HM_LAUNCHED();
+  return 0;
+}
 int conv7x7_bn_relu(cudaStream_t st, const float* images, int B, const float* w, const float* bias, h16* out) {
   conv7x7_kernel<<<blocks_for((size_t)B * 48 * 160 * 8), 256, 0, st>>>(images, B, w, bias, out);
   HM_LAUNCHED();

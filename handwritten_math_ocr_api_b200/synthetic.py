@@ -230,6 +230,15 @@ def synth_images(batch: int, seed: int = 1234) -> torch.Tensor:
     return torch.from_numpy(out)
 
 
+def synth_images_u8(batch: int, seed: int = 1234) -> torch.Tensor:
+    """The same images before the reference transform: uint8 [B,96,320] (255 = paper, 0 = ink)."""
+    out = np.empty((batch, IMG_H, IMG_W), np.uint8)
+    for i in range(batch):
+        rs = np.random.RandomState((seed * 1000003 + i) % (2 ** 31 - 1))
+        out[i] = synth_stroke_image_u8(rs)
+    return torch.from_numpy(out)
+
+
 def synth_vocab(vocab_size: int):
     """vocab / idx2char in the reference's ``vocab.json`` shape
     (``/root/reference/app/src/utils.py:10-15``, specials first: ``src/config.py:43-47``)."""

@@ -117,6 +117,17 @@ int hmocr_generate_host(hmocr_engine* e, const float* images_host, int batch, in
                         int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
                         void* stream);
 
+/* The tail of the reference's preprocessing on the device: ToTensor + Normalize(0.5, 0.5)
+ * (/root/reference/app/src/preprocess.py:7-12, src/predict.py:36-41) of grayscale uint8 images that are already
+ * 96 x 320: images_u8_dev uint8 [B,96,320] -> images_dev f32 [B,1,96,320] = (u/255 - 0.5)/0.5, bit-identical to
+ * torchvision (the PIL resize stays on the host). */
+int hmocr_preprocess_u8(hmocr_engine* e, const uint8_t* images_u8_dev, int batch, float* images_dev, void* stream);
+
+/* hmocr_generate_host with uint8 images (4x less host-to-device traffic): H2D, preprocess, generate, D2H, sync. */
+int hmocr_generate_host_u8(hmocr_engine* e, const uint8_t* images_u8_host, int batch, int max_len, int beam,
+                           int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
+                           void* stream);
+
 /* Phase timings of the last hmocr_generate* call on this engine, measured with CUDA events on
  * the caller's stream (valid after the stream has been synchronised): encoder ms, decode ms. */
 int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_ms);

@@ -388,3 +388,17 @@ def test_decode_is_bitwise_repeatable(model, beam):
             ref = cur
         else:
             assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])
+
+
+def test_device_preprocessing_is_bit_identical_to_the_reference_transform(model):
+    """ToTensor + Normalize(0.5, 0.5) (app/src/preprocess.py:7-12) on uint8 images, on the device."""
+    from handwritten_math_ocr_api_b200.preprocess import preprocess_u8
+    from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_images_u8
+    from torchvision import transforms
+    u8 = synth_images_u8(3, seed=1234)
+    u8[0, :2, :256] = torch.arange(256, dtype=torch.uint8)          # every byte value
+    got = preprocess_u8(model, u8).cpu()
+    norm = transforms.Normalize(mean=[0.5], std=[0.5])
+    ref = torch.stack([norm(transforms.functional.to_tensor(img.numpy()[:, :, None])) for img in u8])
+    assert got.shape == ref.shape == (3, 1, 96, 320) and torch.equal(got, ref)
+    assert torch.equal(synth_images(3, seed=1234)[1:], got[1:])       # = the float images the benchmark feeds
