@@ -683,10 +683,10 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.ctx[0][0], lane, acc);
           const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
-          slot_release();
           stage_tile(j, acc, b0, b1);
           named_bar_sync(1, 64);
           send_y(j * 32 + lane, false);
+          slot_release();                          // peers wait for y: send first, re-arm the weight slot after
         }
         g += 2;
       }
@@ -730,10 +730,10 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.ctx[0][0], lane, acc);
           const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
-          slot_release();
           stage_tile(j, acc, b0, b1);
           named_bar_sync(1, 64);
           send_y(j * 32 + lane, false);
+          slot_release();                          // peers wait for y: send first, re-arm the weight slot after
         }
         g += 2;
       }
@@ -752,7 +752,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           slot_wait();
           gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
           const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
-          slot_release();
           __half(*hs)[72] = reinterpret_cast<__half(*)[72]>(&s.stg[0][0][0]);
           hs[r0][f] = to_half_sat(fmaxf(acc[0] + b0, 0.f)); hs[r0 + 1][f] = to_half_sat(fmaxf(acc[1] + b0, 0.f));
           hs[r0][f + 8] = to_half_sat(fmaxf(acc[2] + b1, 0.f)); hs[r0 + 1][f + 8] = to_half_sat(fmaxf(acc[3] + b1, 0.f));
@@ -761,6 +760,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
             const int u = j * 32 + lane, r = u >> 3, piece = u & 7;
             send_all(&s.hf[r][c * 64 + piece * 8], *reinterpret_cast<const uint4*>(&hs[r][piece * 8]), X_HF);
           }
+          slot_release();
         }
         g += 4;
       }
@@ -775,10 +775,10 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           slot_wait();
           gemm16<PF>(s.slot[warp], &s.hf[0][(j & 1) * 256], lane, acc);
           const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);   // zero in the kh = 1 chunk
-          slot_release();
           stage_tile(j, acc, b0, b1);
           named_bar_sync(3, 128);
           if (j < 2) send_y(j * 32 + lane, true);
+          slot_release();
         }
         g += 4;
       }
