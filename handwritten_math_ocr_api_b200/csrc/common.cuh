@@ -111,6 +111,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same contract, for waits that are expected to be long (a whole tile): the try_wait carries a suspend-time
+// hint so the spinning warp gives its issue slots to the warps that share its scheduler, and the bound is a
+// spin count instead of a clock read per iteration.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+    if (++spins > 50000000u) {
+      printf("hmocr: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -182,20 +205,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 // ---- small math ---------------------------------------------------------------------------------
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level): 2 MUFU + ~12 FMA-class
-// instructions instead of erff()'s branchy ~30.  nn.GELU() is the exact erf form (swin_transformer.py:444).
-__device__ __forceinline__ float erf_as(float x) {
+// nn.GELU() is the exact erf form x * Phi(x) (swin_transformer.py:444).  Phi(-a) for a >= 0 is evaluated as
+// 2^q(a), q a degree-6 minimax polynomial fitted to log2 Phi(-a) on [0, 6] under the weight a * Phi(-a) (the
+// sensitivity of the activation to q; scratch/fit_gelu.py), so that
+//     gelu(x) = max(x, 0) - |x| * 2^q(min(|x|, 6))
+// costs 6 FMA + 1 MUFU.EX2 + 3 ALU.  Max |error| 2.9e-7 over all x (fp32 rounding of the result), relative
+// error < 5e-6 for |x| < 1; beyond |x| = 6 the correction term is below 1e-8 * |x|.
+__device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
+  const float a = fminf(ax, 6.0f);
+  float q = fmaf(3.309328148e-05f, a, -7.692237894e-04f);
+  q = fmaf(q, a, 8.080729945e-03f);
+  q = fmaf(q, a, -5.341212484e-02f);
+  q = fmaf(q, a, -4.587709581e-01f);
+  q = fmaf(q, a, -1.151201707e+00f);
+  q = fmaf(q, a, -9.999930605e-01f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
-  return copysignf(fmaf(-p * t, e, 1.0f), x);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-ax, e, fmaxf(x, 0.0f));
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -6,19 +6,18 @@
 // /root/reference/src/model_swin.py:45,64,87; torch MultiheadAttention in/out projections,
 // TransformerDecoderLayer.linear1/linear2).
 //
-// Structure (one CTA per SM, 320 threads):
-//   warp 0     TMA producer: cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles
-//              into a STAGES-deep shared-memory ring, completion on "full" mbarriers
-//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
-//              tcgen05.commit releases the ring slot ("empty") and publishes the accumulator
-//   warps 2-9  epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row per
-//              thread), fuse bias / GELU / ReLU / fp32 residual / LayerNorm, store fp32 and/or fp16.
-//              A warp may only touch TMEM lanes [32*(warp%4), +32), so two warps share each lane
-//              quarter and take alternate 32-column chunks: the small-K GEMMs of Swin stage 1/2 are
-//              epilogue-bound, and one epilogue warp per scheduler cannot hide its own latencies.
-// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i overlap the main loop of
-// tile i+1; the producer runs ahead across tile boundaries, so HBM stays busy for the small-K
-// shapes of Swin stage 1/2 where the epilogue dominates.
+// Structure (one CTA per SM, 576 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles
+//               into a STAGES-deep shared-memory ring, completion on "full" mbarriers
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
+//               tcgen05.commit releases the ring slot ("empty") and publishes the accumulator
+//   warps 2-17  epilogue, two groups of eight.  The Swin GEMMs have K = 96..768: their main loop is a few
+//               hundred cycles per tile and the time goes into reading 128 x BN accumulators out of TMEM,
+//               applying bias / GELU / residual and writing them coalesced.  So there are two TMEM
+//               accumulators, group g owns accumulator g and takes every second tile of the CTA (two tiles
+//               are in the epilogue at once while the main loop of the following ones runs), and inside a
+//               group two warps share each TMEM lane quarter (a warp may only touch lanes
+//               [32*(warp%4), +32)) and take alternate 32-column chunks.
 #include "gemm.cuh"
 
 #include <map>
@@ -30,25 +29,30 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 16;                 // two groups of eight
+constexpr int GROUP_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int EPI_WARP_BYTES = 4096 + 128;    // one 32 x 32 fp32 transpose tile + 32 bias values per epilogue warp
 
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 32 * 4;      // one 32 x 32 fp32 transpose tile per epilogue warp
-  static constexpr int STAGES_RAW = (190 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int STAGES_RAW = (156 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_STAGE_BYTES;
 };
 
+enum EpiMode { EPI_GENERAL = 0, EPI_F16 = 1, EPI_LN = 2 };
+
 struct GemmParams {
   int M, N, K;
   int num_n_tiles, num_tiles;
+  int mode;           // EpiMode, chosen on the host from the epilogue description
   int dbg;            // timing experiments only: 1 = skip output stores, 2 = skip residual loads, 4 = skip the epilogue math
   GemmEpilogue epi;
 };
@@ -74,32 +78,90 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
          | (uint32_t(BM >> 4) << 24);  // M
 }
 
-// Plain epilogue of one 32-row x BN-column slab (this warp's TMEM lane quarter), 32 columns at a time.
-// tcgen05.ld hands every thread one ROW (32 consecutive fp32 of it); global memory wants the opposite: a warp
-// instruction that covers whole rows.  So the raw accumulators go through a 4 KB per-warp shared tile
-// (16-byte chunks XOR-swizzled by row: conflict-free both ways) and come back with lane = (row % 4, 4-column
-// group): every load of the fp32 residual and every store is 4 rows x 128 contiguous bytes (fp16: x 64) instead
-// of 32 scattered 16-byte pieces.  Bias, activation and residual are applied in that second layout, where a
-// lane owns the same 4 columns for all 32 rows (one bias load per chunk).  The residual loads are issued before
-// the TMEM load so their latency overlaps it.
-template <int BN>
-__device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t taddr, float* stage, int m_base,
-                                               int M, int n0, int c_first, int dbg) {
+// fp16-output epilogue (qkv, fc1 + GELU, linear1 + ReLU: no residual, no fp32 copy) of one 32-row x BN-column
+// slab, 32 columns at a time.  tcgen05.ld hands every thread one ROW (32 consecutive fp32 of it); bias and
+// activation are applied right there, as 32 independent chains per thread (the bias values of the chunk are
+// broadcast from a 128-byte shared slot), and the row is packed to 64 bytes of fp16.  Global memory wants the
+// opposite of one-row-per-thread: a warp instruction that covers whole rows.  So the packed rows go through a
+// 2 KB per-warp shared tile (16-byte pieces XOR-swizzled by row: conflict-free both ways) and leave as four
+// 16-byte stores per thread, each warp store covering 8 rows x 64 contiguous bytes.
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
+                                             int M, int n0, int c_first, int dbg) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t bias_addr = st_addr + 4096;
+  const int srow = lane >> 2, sq = lane & 3;              // store layout: rows it*8 + srow, 16-byte piece sq
+  const uint32_t wr_addr = st_addr + lane * 64, wr_sw = (lane >> 1) & 3;
+  const uint32_t rd_addr = st_addr + srow * 64 + ((sq ^ ((srow >> 1) & 3)) << 4);
+  h16* out = e.out_f16 + (size_t)(m_base + srow) * e.ld16 + n0 + sq * 8;
+  const size_t out_step = (size_t)8 * e.ld16;
+  const int rows_left = (dbg & 1) ? 0 : M - m_base - srow;       // row it*8 + srow exists iff it*8 < rows_left
+#pragma unroll 1
+  for (int c = c_first; c < BN / 32; c += 2) {
+    const float b = e.bias != nullptr ? __ldg(e.bias + n0 + c * 32 + lane) : 0.0f;
+    __syncwarp();                                        // the previous chunk has been read out of tile and bias slot
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_addr + lane * 4), "f"(b) : "memory");
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    if ((dbg & 4) && r[0] != 0x12345678u) continue;      // timing experiment: main loop + TMEM load only
+    __syncwarp();
+    uint32_t h[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 bq;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
+                   : "r"(bias_addr + q * 16));
+      float v0 = __uint_as_float(r[4 * q]) + bq.x, v1 = __uint_as_float(r[4 * q + 1]) + bq.y;
+      float v2 = __uint_as_float(r[4 * q + 2]) + bq.z, v3 = __uint_as_float(r[4 * q + 3]) + bq.w;
+      if (ACT == 1) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3); }
+      if (ACT == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+      h[2 * q] = pack16(v0, v1);
+      h[2 * q + 1] = pack16(v2, v3);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr_addr + ((q ^ wr_sw) << 4)), "r"(h[4 * q]),
+                   "r"(h[4 * q + 1]), "r"(h[4 * q + 2]), "r"(h[4 * q + 3])
+                   : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(rd_addr + it * 512));
+      if (it * 8 < rows_left) *reinterpret_cast<uint4*>(out + it * out_step + c * 32) = v;
+    }
+  }
+}
+
+// General epilogue (fp32 output and/or fp32 residual; ReLU before or after the residual add): the raw
+// accumulators go through a 4 KB per-warp shared tile (16-byte chunks XOR-swizzled by row) and come back with
+// lane = (row % 4, 4-column group), so every load of the fp32 residual and every store is 4 rows x 128
+// contiguous bytes (fp16 copy: x 64) instead of 32 scattered 16-byte pieces.  Bias, activation and residual are
+// applied in that second layout, where a lane owns the same 4 columns for all 32 rows (one bias load per
+// chunk).  The residual loads are issued before the TMEM load so their latency overlaps it.
+template <int BN, bool RES>
+__device__ __forceinline__ void epilogue_general(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
+                                                 int M, int n0, int c_first, int dbg) {
   const int lane = threadIdx.x & 31;
   const int rr = lane >> 3, cg = lane & 7;            // second layout: row (it*4 + rr), columns 4*cg .. 4*cg+3
-  const uint32_t st_addr = smem_u32(stage);
+  const float lo_pre = e.act == 2 ? 0.0f : -INFINITY, lo_post = e.act == 3 ? 0.0f : -INFINITY;
+  const int rows_left = M - m_base - rr;              // row it*4 + rr exists iff it*4 < rows_left
+  const int rows_store = (dbg & 1) ? 0 : rows_left;
+  const uint32_t wr_addr = st_addr + lane * 128, wr_sw = lane & 7;
+  const uint32_t rd_addr = st_addr + rr * 128;        // + it*512 + ((cg ^ ((it*4 + rr) & 7)) << 4)
 #pragma unroll 1
   for (int c = c_first; c < BN / 32; c += 2) {
     const int col = n0 + c * 32 + cg * 4;
     float4 res[8];
-    const bool has_res = e.residual != nullptr && !(dbg & 2);
-    if (has_res) {
+    if (RES) {
+      const float* rp = e.residual + (size_t)(m_base + rr) * e.ldr + col;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = m_base + it * 4 + rr;
-        res[it] = (row < M) ? __ldcs(reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldr + col))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int it = 0; it < 8; ++it)
+        res[it] = (it * 4 < rows_left) ? __ldcs(reinterpret_cast<const float4*>(rp + (size_t)it * 4 * e.ldr))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
@@ -109,26 +171,27 @@ __device__ __forceinline__ void epilogue_plain(const GemmEpilogue& e, uint32_t t
     __syncwarp();                                      // the previous chunk has been read out of the tile
 #pragma unroll
     for (int q = 0; q < 8; ++q)                        // thread = row `lane`: chunk q -> physical chunk q ^ (lane & 7)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + lane * 128 + ((q ^ (lane & 7)) << 4)),
-                   "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr_addr + ((q ^ wr_sw) << 4)), "r"(r[4 * q]),
+                   "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
                    : "memory");
     __syncwarp();
+    float* o32 = e.out_f32 != nullptr ? e.out_f32 + (size_t)(m_base + rr) * e.ld32 + col : nullptr;
+    h16* o16 = e.out_f16 != nullptr ? e.out_f16 + (size_t)(m_base + rr) * e.ld16 + col : nullptr;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int lr = it * 4 + rr, row = m_base + lr;
       float4 v;
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                    : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "r"(st_addr + lr * 128 + ((cg ^ (lr & 7)) << 4)));
+                   : "r"(rd_addr + it * 512 + ((cg ^ ((it * 4 + rr) & 7)) << 4)));
       v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
       if (e.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-      else if (e.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      if (has_res) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
-      if (e.act == 3) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      if (row < M && !((dbg & 1) && v.x != 12345.678f)) {
-        if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld32 + col) = v;
-        if (e.out_f16 != nullptr)
-          *reinterpret_cast<uint2*>(e.out_f16 + (size_t)row * e.ld16 + col) = make_uint2(pack16(v.x, v.y), pack16(v.z, v.w));
+      v.x = fmaxf(v.x, lo_pre); v.y = fmaxf(v.y, lo_pre); v.z = fmaxf(v.z, lo_pre); v.w = fmaxf(v.w, lo_pre);
+      if (RES) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+      v.x = fmaxf(v.x, lo_post); v.y = fmaxf(v.y, lo_post); v.z = fmaxf(v.z, lo_post); v.w = fmaxf(v.w, lo_post);
+      if (it * 4 < rows_store) {
+        if (o32 != nullptr) *reinterpret_cast<float4*>(o32 + (size_t)it * 4 * e.ld32) = v;
+        if (o16 != nullptr)
+          *reinterpret_cast<uint2*>(o16 + (size_t)it * 4 * e.ld16) = make_uint2(pack16(v.x, v.y), pack16(v.z, v.w));
       }
     }
   }
@@ -221,7 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);   // 1024-aligned
+  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -235,7 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);
+      mbar_init(&tempty_bar[a], GROUP_WARPS);
     }
     fence_barrier_init();
   }
@@ -272,7 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[a], aph ^ 1u);
+        mbar_wait_backoff(&tempty_bar[a], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -292,27 +355,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    const int quarter = warp & 3;        // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-    int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const int a = it & 1;
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int ew = warp - 2;
+    const int group = ew >> 3;             // accumulator / tile parity this warp serves
+    const int half = (ew >> 2) & 1;        // which of the two warps of this lane quarter inside the group
+    const uint32_t st_addr = epi_stage + ew * EPI_WARP_BYTES;
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + group * BN;
+    const bool has_res = p.epi.residual != nullptr && !(p.dbg & 2);
+    int it = group;
+    for (int t = blockIdx.x + group * gridDim.x; t < p.num_tiles; t += 2 * gridDim.x, it += 2) {
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (t / p.num_n_tiles) * BM;
       const int n0 = (t % p.num_n_tiles) * BN;
-      mbar_wait(&tfull_bar[a], aph);
+      mbar_wait_backoff(&tfull_bar[group], aph);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BN;
-      const int half = (warp - 2) >> 2;    // which of the two warps of this lane quarter
-      if (p.epi.ln_gamma != nullptr) {
-        if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row_ok, n0);     // row statistics: one thread per row
+      const int mb = m0 + quarter * 32;
+      if (p.mode == EPI_LN) {
+        const int row = mb + lane;
+        if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row < p.M, n0);   // row statistics: one thread per row
+      } else if (p.mode == EPI_F16) {
+        if (p.epi.act == 1) epilogue_f16<BN, 1>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
+        else if (p.epi.act == 2) epilogue_f16<BN, 2>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
+        else epilogue_f16<BN, 0>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
       } else {
-        epilogue_plain<BN>(p.epi, taddr, epi_stage + (warp - 2) * 1024, m0 + quarter * 32, p.M, n0, half, p.dbg);
+        if (has_res) epilogue_general<BN, true>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
+        else epilogue_general<BN, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (lane == 0) mbar_arrive(&tempty_bar[group]);
     }
   }
 
@@ -372,6 +443,8 @@ int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* 
   p.num_tiles = ceil_div(M, BM) * p.num_n_tiles;
   p.epi = epi;
   p.dbg = g_gemm_dbg;
+  p.mode = epi.ln_gamma != nullptr ? EPI_LN
+           : (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
   HM_LAUNCHED();
