@@ -225,6 +225,43 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-ax, e, fmaxf(x, 0.0f));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: two lanes of fp32 per issue slot).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_erf on two values at once: same polynomial, the Horner chain in FFMA2 (bit-identical to gelu_erf).
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float ax0 = fabsf(x0), ax1 = fabsf(x1);
+  const uint64_t a = pk2(fminf(ax0, 6.0f), fminf(ax1, 6.0f));
+  uint64_t q = fma2(pk2(3.309328148e-05f, 3.309328148e-05f), a, pk2(-7.692237894e-04f, -7.692237894e-04f));
+  q = fma2(q, a, pk2(8.080729945e-03f, 8.080729945e-03f));
+  q = fma2(q, a, pk2(-5.341212484e-02f, -5.341212484e-02f));
+  q = fma2(q, a, pk2(-4.587709581e-01f, -4.587709581e-01f));
+  q = fma2(q, a, pk2(-1.151201707e+00f, -1.151201707e+00f));
+  q = fma2(q, a, pk2(-9.999930605e-01f, -9.999930605e-01f));
+  float q0, q1, e0, e1;
+  upk2(q, q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const uint64_t o = fma2(pk2(-ax0, -ax1), pk2(e0, e1), pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  upk2(o, x0, x1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

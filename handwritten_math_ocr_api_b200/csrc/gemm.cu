@@ -78,6 +78,15 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
          | (uint32_t(BM >> 4) << 24);  // M
 }
 
+// Epilogue warps hand their TMEM accumulator back as soon as its last chunk has been loaded into registers
+// (the bias/activation/store work of that chunk then overlaps the next main loop).  The __syncwarp doubles as
+// the "bias slot is written" fence of the fp16 path.
+__device__ __forceinline__ void release_accumulator(bool last_chunk, uint64_t* release_bar) {
+  tc_fence_before();
+  __syncwarp();
+  if (last_chunk && (threadIdx.x & 31) == 0) mbar_arrive(release_bar);
+}
+
 // fp16-output epilogue (qkv, fc1 + GELU, linear1 + ReLU: no residual, no fp32 copy) of one 32-row x BN-column
 // slab, 32 columns at a time.  tcgen05.ld hands every thread one ROW (32 consecutive fp32 of it); bias and
 // activation are applied right there, as 32 independent chains per thread (the bias values of the chunk are
@@ -87,7 +96,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 // 16-byte stores per thread, each warp store covering 8 rows x 64 contiguous bytes.
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
-                                             int M, int n0, int c_first, int dbg) {
+                                             int M, int n0, int c_first, int dbg, uint64_t* release_bar) {
   const int lane = threadIdx.x & 31;
   const uint32_t bias_addr = st_addr + 4096;
   const int srow = lane >> 2, sq = lane & 3;              // store layout: rows it*8 + srow, 16-byte piece sq
@@ -103,18 +112,17 @@ __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t tad
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_addr + lane * 4), "f"(b) : "memory");
     uint32_t r[32];
     tmem_ld32(taddr + c * 32, r);
+    release_accumulator(c + 2 >= BN / 32, release_bar);  // the last chunk is in registers: the MMA warp may reuse the columns
     if ((dbg & 4) && r[0] != 0x12345678u) continue;      // timing experiment: main loop + TMEM load only
-    __syncwarp();
     uint32_t h[16];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float4 bq;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
-                   : "r"(bias_addr + q * 16));
-      float v0 = __uint_as_float(r[4 * q]) + bq.x, v1 = __uint_as_float(r[4 * q + 1]) + bq.y;
-      float v2 = __uint_as_float(r[4 * q + 2]) + bq.z, v3 = __uint_as_float(r[4 * q + 3]) + bq.w;
-      if (ACT == 1) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3); }
+      uint64_t b01, b23;
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bias_addr + q * 16));
+      float v0, v1, v2, v3;
+      upk2(add2(pk2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), b01), v0, v1);
+      upk2(add2(pk2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), b23), v2, v3);
+      if (ACT == 1) { gelu_erf2(v0, v1); gelu_erf2(v2, v3); }
       if (ACT == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
       h[2 * q] = pack16(v0, v1);
       h[2 * q + 1] = pack16(v2, v3);
@@ -144,7 +152,7 @@ __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t tad
 // chunk).  The residual loads are issued before the TMEM load so their latency overlaps it.
 template <int BN, bool RES>
 __device__ __forceinline__ void epilogue_general(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
-                                                 int M, int n0, int c_first, int dbg) {
+                                                 int M, int n0, int c_first, int dbg, uint64_t* release_bar) {
   const int lane = threadIdx.x & 31;
   const int rr = lane >> 3, cg = lane & 7;            // second layout: row (it*4 + rr), columns 4*cg .. 4*cg+3
   const float lo_pre = e.act == 2 ? 0.0f : -INFINITY, lo_post = e.act == 3 ? 0.0f : -INFINITY;
@@ -167,8 +175,8 @@ __device__ __forceinline__ void epilogue_general(const GemmEpilogue& e, uint32_t
     if (e.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
     uint32_t r[32];
     tmem_ld32(taddr + c * 32, r);
+    release_accumulator(c + 2 >= BN / 32, release_bar);   // also: the previous chunk has been read out of the tile
     if ((dbg & 4) && r[0] != 0x12345678u) continue;    // timing experiment: main loop + TMEM load only
-    __syncwarp();                                      // the previous chunk has been read out of the tile
 #pragma unroll
     for (int q = 0; q < 8; ++q)                        // thread = row `lane`: chunk q -> physical chunk q ^ (lane & 7)
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr_addr + ((q ^ wr_sw) << 4)), "r"(r[4 * q]),
@@ -374,16 +382,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row = mb + lane;
         if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row < p.M, n0);   // row statistics: one thread per row
       } else if (p.mode == EPI_F16) {
-        if (p.epi.act == 1) epilogue_f16<BN, 1>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
-        else if (p.epi.act == 2) epilogue_f16<BN, 2>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
-        else epilogue_f16<BN, 0>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
+        if (p.epi.act == 1) epilogue_f16<BN, 1>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
+        else if (p.epi.act == 2) epilogue_f16<BN, 2>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
+        else epilogue_f16<BN, 0>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
       } else {
-        if (has_res) epilogue_general<BN, true>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
-        else epilogue_general<BN, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg);
+        if (has_res) epilogue_general<BN, true>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
+        else epilogue_general<BN, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[group]);
+      if (p.mode == EPI_LN) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[group]);
+      }
     }
   }
 
