@@ -1,16 +1,19 @@
 // Fused shifted-window attention on tensor cores (sm_100a).            swin_transformer.py:151-214,219-227
 //
-// One WARP = one (window, head) at a time, looping over windows with a fixed head so the head's
-// relative-position bias [49][49] stays in the warp's private shared memory.  Per item:
+// One WARP = one (window, head) at a time.  The eight warps of a CTA work on the SAME head, so the head's
+// relative-position bias [49][49] sits once in the CTA's shared memory; each warp loops over windows with
+// private 49-row Q/K/V tiles (12 KB), which leaves room for 16 warps per SM.  Per item:
 //   * the cyclic shift, zero padding, window partition and their inverses are index arithmetic on
 //     the un-shifted, un-padded qkv buffer (rolled position (r,c) reads padded position
 //     ((r+sh)%Hp, (c+sw)%Wp)); a padded token has q = k = v = qkv.bias; its output is never written;
-//   * Q, K, V rows (49 x 32 fp16 each) are gathered with 16-byte cp.async into padded 64x40 tiles;
+//   * Q, K, V rows (49 x 32 fp16 each) are gathered with 16-byte cp.async, 8 tokens x 4 pieces per pass;
+//     the rows 49..63 the 16-row MMA tiles reach for are one shared 16-byte line of zeros (every lane
+//     hands ldmatrix its own row address);
 //   * S = Q K^T (mma.sync m16n8k16, 4 m-tiles x 7 n-tiles x 2 k-steps), scaled by 32^-0.5, plus bias,
 //     plus the -100 region mask; softmax in fp32 registers with quad shuffles;
 //   * O = P V with P re-packed from the S accumulators straight into A fragments and V read through
 //     ldmatrix.trans; rows are normalised and scattered back to the original token order.
-// No block-level synchronisation at all: every warp owns its tiles (__syncwarp only).
+// One __syncthreads (the bias table); after that every warp owns its tiles (__syncwarp only).
 // 96.5 % of the encoder FLOPs are the tcgen05 GEMMs; this kernel's job is to stop the 49x49
 // attention + the roll/partition copies from costing more time than they do FLOPs.
 #include "kernels.cuh"
@@ -21,15 +24,19 @@ namespace {
 constexpr int WS = 7, WN = 49, HD = 32;
 constexpr int TP = 40;            // tile pitch (fp16): 80-byte rows are conflict-free for ldmatrix
 constexpr int BP = 52;            // bias pitch (fp32)
-constexpr int WARPS = 4;
+constexpr int WARPS = 8;
 
 struct WarpTile {
-  h16 q[64][TP];
-  h16 k[64][TP];
-  h16 v[64][TP];
-  float bias[WN][BP];
-  int tok[64];       // token row in the qkv buffer, -1 if padded
-  int region[64];
+  h16 q[WN][TP];
+  h16 k[WN][TP];
+  h16 v[WN][TP];
+  int tok[WN + 3];            // token row in the qkv buffer, -1 if padded
+  uint8_t region[64];
+};
+struct CtaShared {
+  float bias[WN][BP];         // this head's relative-position bias, times log2(e)
+  uint4 zero[4];              // what ldmatrix reads for tile rows >= 49 (64 bytes: a row address may be advanced by 32)
+  WarpTile w[WARPS];
 };
 
 __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
@@ -59,20 +66,20 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* __restrict__ qkv,
-                                                                     const float* __restrict__ qkv_bias,
-                                                                     const float* __restrict__ rel_bias, int B, int H,
-                                                                     int W, int C, int heads, int sh, int sw, int Hp,
-                                                                     int Wp, h16* __restrict__ ctx) {
+__global__ void __launch_bounds__(WARPS * 32, 2) window_attn_mma_kernel(const h16* __restrict__ qkv,
+                                                                        const float* __restrict__ qkv_bias,
+                                                                        const float* __restrict__ rel_bias, int B, int H,
+                                                                        int W, int C, int heads, int sh, int sw, int Hp,
+                                                                        int Wp, h16* __restrict__ ctx) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  CtaShared& cs = *reinterpret_cast<CtaShared*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpTile& s = reinterpret_cast<WarpTile*>(smem_raw)[warp];
-  const int gw = blockIdx.x * WARPS + warp;
-  const int per_head = (gridDim.x * WARPS) / heads;          // warps working on one head
-  if (per_head == 0 || gw >= per_head * heads) return;
-  const int h = gw % heads;
+  WarpTile& s = cs.w[warp];
+  const int per_head = gridDim.x / heads;                    // CTAs working on one head
+  if (per_head == 0 || (int)blockIdx.x >= per_head * heads) return;
+  const int h = blockIdx.x % heads;
   const int g4 = lane >> 2, t4 = lane & 3;
-  const int nww = Wp / WS, nwin = (Hp / WS) * nww;
+  const int nww = Wp / WS, nwh = Hp / WS, nwin = nwh * nww;
   const int total = B * nwin;
   const bool masked = (sh + sw) > 0;
   // softmax on ex2: log2(e) is folded into the q scale (32^-0.5, swin_transformer.py:188), the bias table and the mask
@@ -80,52 +87,66 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
   const float scale = 0.17677669529663687f * LOG2E;
   const float mask_val = -100.0f * LOG2E;
 
-  // one-time: zero the padding rows (finite operands for the masked / zero-probability lanes) and
-  // fetch this head's relative-position bias
-  for (int i = lane; i < 15 * TP; i += 32) {
-    (&s.k[WN][0])[i] = to_h16(0.f);
-    (&s.v[WN][0])[i] = to_h16(0.f);
-    (&s.q[WN][0])[i] = to_h16(0.f);
+  for (int i = threadIdx.x; i < WN * WN; i += WARPS * 32)
+    cs.bias[i / WN][i % WN] = __ldg(rel_bias + (size_t)h * WN * WN + i) * LOG2E;
+  for (int i = threadIdx.x; i < WN; i += WARPS * 32) cs.bias[i][WN] = 0.f;   // column 49 is read (and discarded) by the float2 loads
+  if (threadIdx.x < 4) cs.zero[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+  // q = k = v of a padded token: this head's slice of qkv.bias, the 16-byte piece this lane copies
+  uint4 padv[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(qkv_bias + m * C + h * HD + t4 * 8));
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(qkv_bias + m * C + h * HD + t4 * 8 + 4));
+    padv[m] = make_uint4(pack16(a.x, a.y), pack16(a.z, a.w), pack16(c4.x, c4.y), pack16(c4.z, c4.w));
   }
-  for (int i = lane; i < WN * WN; i += 32) s.bias[i / WN][i % WN] = __ldg(rel_bias + (size_t)h * WN * WN + i) * LOG2E;
-  for (int i = lane; i < WN; i += 32) s.bias[i][WN] = 0.f;     // column 49 is read (and discarded) by the float2 loads
-  __syncwarp();
+  __syncthreads();
 
-  for (int wi = gw / heads; wi < total; wi += per_head) {
+  const uint32_t zero_addr = smem_u32(&cs.zero[0]);
+  const uint32_t q_addr = smem_u32(&s.q[0][0]), k_addr = smem_u32(&s.k[0][0]), v_addr = smem_u32(&s.v[0][0]);
+  // ldmatrix row addresses of this lane (tile rows 0..47 are real; of rows 48..63 only row 48 exists)
+  const uint32_t q_lane = q_addr + (lane & 15) * (TP * 2) + (lane >> 4) * 16;
+  const uint32_t q_last = (lane & 15) == 0 ? q_addr + 48 * (TP * 2) + (lane >> 4) * 16 : zero_addr;
+  const uint32_t k_lane = k_addr + (lane & 7) * (TP * 2) + ((lane >> 3) & 1) * 16;
+  const uint32_t k_last = (lane & 7) == 0 ? k_addr + 48 * (TP * 2) + ((lane >> 3) & 1) * 16 : zero_addr;
+  const uint32_t v_lane = v_addr + (lane & 15) * (TP * 2);
+  const bool v_last_ok = (lane & 15) == 0;
+
+  const int item0 = (blockIdx.x / heads) * WARPS + warp, item_step = per_head * WARPS;
+  for (int wi = item0; wi < total; wi += item_step) {
     const int b = wi / nwin, win = wi - b * nwin;
     const int wr = win / nww, wc = win - wr * nww;
-    for (int p = lane; p < WN; p += 32) {
-      const int r = wr * WS + p / WS, c = wc * WS + p % WS;        // rolled, padded coordinates
-      const int pr = (r + sh) % Hp, pc = (c + sw) % Wp;            // padded coordinates before the roll
-      s.tok[p] = (pr < H && pc < W) ? (b * H + pr) * W + pc : -1;
-      int reg = 0;
-      if (masked) {
-        // slices (0,-7),(-7,-s),(-s,None) written in order; s == 0 makes the last one cover everything
-        const int hb = (sh == 0) ? 2 : ((r >= Hp - WS) + (r >= Hp - sh));
-        const int wb = (sw == 0) ? 2 : ((c >= Wp - WS) + (c >= Wp - sw));
-        reg = hb * 3 + wb;
-      }
-      s.region[p] = reg;
-    }
-    __syncwarp();
-    // most windows lie in ONE region of the shift mask (only the last window row / column is cut): warp-uniform test
-    bool mixed = false;
-    if (masked) {
-      const int r0 = s.region[0];
-      mixed = __any_sync(0xffffffffu, s.region[lane] != r0 || s.region[min(lane + 32, WN - 1)] != r0);
-    }
-    for (int i = lane; i < WN * 12; i += 32) {
-      const int p = i / 12, m = (i % 12) >> 2, ch = i & 3;
-      h16* dst = (m == 0 ? &s.q[p][0] : (m == 1 ? &s.k[p][0] : &s.v[p][0])) + ch * 8;
-      const int col = m * C + h * HD + ch * 8;
-      const int tok = s.tok[p];
-      if (tok >= 0) {
-        cp_async16(dst, qkv + (size_t)tok * 3 * C + col);
-      } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(qkv_bias + col));
-        const float4 c4 = __ldg(reinterpret_cast<const float4*>(qkv_bias + col + 4));
-        *reinterpret_cast<uint4*>(dst) =
-            make_uint4(pack16(a.x, a.y), pack16(a.z, a.w), pack16(c4.x, c4.y), pack16(c4.z, c4.w));
+    // most windows lie in ONE region of the shift mask: only the last window row / column is cut by the roll
+    const bool mixed = masked && ((sh > 0 && wr == nwh - 1) || (sw > 0 && wc == nww - 1));
+#pragma unroll
+    for (int pass = 0; pass < 7; ++pass) {
+      const int p = pass * 8 + g4;                               // token slot of the window; this lane copies piece t4
+      if (p < WN) {
+        const int pi = (p * 37) >> 8;                            // p / 7 for p < 64
+        const int r = wr * WS + pi, c = wc * WS + (p - pi * WS); // rolled, padded coordinates
+        int pr = r + sh, pc = c + sw;                            // padded coordinates before the roll
+        if (pr >= Hp) pr -= Hp;
+        if (pc >= Wp) pc -= Wp;
+        const int tok = (pr < H && pc < W) ? (b * H + pr) * W + pc : -1;
+        if (t4 == 0) {
+          s.tok[p] = tok;
+          if (mixed) {
+            // slices (0,-7),(-7,-s),(-s,None) written in order; s == 0 makes the last one cover everything
+            const int hb = (sh == 0) ? 2 : ((r >= Hp - WS) + (r >= Hp - sh));
+            const int wb = (sw == 0) ? 2 : ((c >= Wp - WS) + (c >= Wp - sw));
+            s.region[p] = (uint8_t)(hb * 3 + wb);
+          }
+        }
+        const uint32_t off = p * (TP * 2) + t4 * 16;
+        if (tok >= 0) {
+          const h16* src = qkv + (size_t)tok * 3 * C + h * HD + t4 * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q_addr + off), "l"(src) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(k_addr + off), "l"(src + C) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(v_addr + off), "l"(src + 2 * C) : "memory");
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q_addr + off), "r"(padv[0].x), "r"(padv[0].y), "r"(padv[0].z), "r"(padv[0].w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(k_addr + off), "r"(padv[1].x), "r"(padv[1].y), "r"(padv[1].z), "r"(padv[1].w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(v_addr + off), "r"(padv[2].x), "r"(padv[2].y), "r"(padv[2].z), "r"(padv[2].w) : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -134,24 +155,27 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
       uint32_t aq[2][4];
-      ldsm4(smem_u32(&s.q[mt * 16 + (lane & 15)][(lane >> 4) * 8]), aq[0]);
-      ldsm4(smem_u32(&s.q[mt * 16 + (lane & 15)][(lane >> 4) * 8 + 16]), aq[1]);
+      const uint32_t qa = mt < 3 ? q_lane + mt * 16 * (TP * 2) : q_last;
+      ldsm4(qa, aq[0]);
+      ldsm4(qa + 32, aq[1]);
       const int r0 = mt * 16 + g4, r1 = r0 + 8;
       const int rb0 = min(r0, WN - 1), rb1 = min(r1, WN - 1);       // clamp for the bias / region lookups
-      const int reg0 = s.region[rb0], reg1 = s.region[rb1];
+      int reg0 = 0, reg1 = 0;
+      if (mixed) { reg0 = s.region[rb0]; reg1 = s.region[rb1]; }
       float sc[7][4];
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 7; ++nt) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t bk[2];
-        ldsm2(smem_u32(&s.k[nt * 8 + (lane & 7)][((lane >> 3) & 1) * 8]), bk);
+        const uint32_t ka = nt < 6 ? k_lane + nt * 8 * (TP * 2) : k_last;
+        ldsm2(ka, bk);
         mma16816(c, aq[0], bk);
-        ldsm2(smem_u32(&s.k[nt * 8 + (lane & 7)][((lane >> 3) & 1) * 8 + 16]), bk);
+        ldsm2(ka + 32, bk);
         mma16816(c, aq[1], bk);
         const int c0 = nt * 8 + 2 * t4;                      // columns c0, c0 + 1 (c0 is even, <= 54)
-        const float2 b0 = *reinterpret_cast<const float2*>(&s.bias[rb0][min(c0, WN - 1) & ~1]);
-        const float2 b1 = *reinterpret_cast<const float2*>(&s.bias[rb1][min(c0, WN - 1) & ~1]);
+        const float2 b0 = *reinterpret_cast<const float2*>(&cs.bias[rb0][min(c0, WN - 1) & ~1]);
+        const float2 b1 = *reinterpret_cast<const float2*>(&cs.bias[rb1][min(c0, WN - 1) & ~1]);
         float v[4] = {fmaf(c[0], scale, b0.x), fmaf(c[1], scale, b0.y), fmaf(c[2], scale, b1.x), fmaf(c[3], scale, b1.y)};
         if (mixed) {
           const int rc0 = s.region[min(c0, WN - 1)], rc1 = s.region[min(c0 + 1, WN - 1)];
@@ -189,7 +213,9 @@ __global__ void __launch_bounds__(WARPS * 32) window_attn_mma_kernel(const h16* 
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint32_t bv[2];
-          ldsm2_trans(smem_u32(&s.v[kk * 16 + (lane & 15)][nt2 * 8]), bv);
+          const uint32_t va = kk < 3 ? v_lane + kk * 16 * (TP * 2) + nt2 * 16
+                                     : (v_last_ok ? v_addr + 48 * (TP * 2) + nt2 * 16 : zero_addr);
+          ldsm2_trans(va, bv);
           mma16816(o, pa[kk], bv);
         }
         const int col = h * HD + nt2 * 8 + 2 * t4;
@@ -210,16 +236,19 @@ int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, con
   const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;
   const int sh = (Hp > WS) ? shift : 0, sw = (Wp > WS) ? shift : 0;   // swin_transformer.py:158-163
   static bool attr = false;
-  const int smem = WARPS * (int)sizeof(WarpTile);
+  const int smem = (int)sizeof(CtaShared);
   if (!attr) {
     HM_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  const long items = (long)B * (Hp / WS) * (Wp / WS) * heads;
-  int grid = 148 * 2;                                  // 2 CTAs per SM (104 KB each)
-  const int need = (int)((items + WARPS - 1) / WARPS);
-  if (need < grid) grid = need < 1 ? 1 : need;
-  if (grid * WARPS < heads) grid = ceil_div(heads, WARPS);
+  // CTAs are bound to heads (block % heads): 2 CTAs per SM (105 KB each), rounded down to a multiple of heads;
+  // fewer when there are not enough windows to give every warp one.
+  const long windows = (long)B * (Hp / WS) * (Wp / WS);
+  int per_head = (148 * 2) / heads;
+  const int need = (int)((windows + WARPS - 1) / WARPS);
+  if (need < per_head) per_head = need;
+  if (per_head < 1) per_head = 1;
+  const int grid = per_head * heads;
   window_attn_mma_kernel<<<grid, WARPS * 32, smem, st>>>(qkv, qkv_bias, rel_bias, B, H, W, C, heads, sh, sw, Hp, Wp, ctx);
   HM_LAUNCHED();
   return 0;
