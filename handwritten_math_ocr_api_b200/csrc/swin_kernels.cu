@@ -173,48 +173,89 @@ int launch_ln_c(cudaStream_t st, const float* x, int rows, int H, int W, const f
 
 // ------------------------------------------------------------------------------------------
 // Patch embedding: Conv2d(1,96,k4,s4) + NHWC + LayerNorm(96)     swin_transformer.py:556-562
-// one warp per token; lane owns channels lane, lane+32, lane+64
+// One THREAD per token: its 16 pixels in registers, 96 accumulators as 48 fp32 pairs (FFMA2), the
+// transposed conv weight [tap][channel] broadcast from shared memory; the LayerNorm statistics need no
+// shuffles.  A warp's 32 tokens are one contiguous 12 KB block of the output, so the normalised rows go
+// through a padded per-warp shared tile and leave as 24 fully coalesced 512-byte stores.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, int ntok,
-                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                          const float* __restrict__ g, const float* __restrict__ beta,
-                                                          float* __restrict__ x) {
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  float wr[3][16], br[3], gr[3], ber[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int ch = lane + 32 * c;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) wr[c][k] = __ldg(w + ch * 16 + k);
-    br[c] = __ldg(bias + ch);
-    gr[c] = __ldg(g + ch);
-    ber[c] = __ldg(beta + ch);
+constexpr int PE_WARPS = 4, PE_PITCH = 100;
+struct PatchSmem {
+  float wT[16][96];
+  float bias[96], g[96], beta[96];
+  float tile[PE_WARPS][32][PE_PITCH];
+};
+
+__global__ void __launch_bounds__(PE_WARPS * 32, 3) patch_embed_kernel(const float* __restrict__ img, int ntok,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ bias,
+                                                                      const float* __restrict__ g,
+                                                                      const float* __restrict__ beta,
+                                                                      float* __restrict__ x) {
+  extern __shared__ __align__(16) uint8_t pe_raw[];
+  PatchSmem& s = *reinterpret_cast<PatchSmem*>(pe_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 96 * 16; i += PE_WARPS * 32) s.wT[i & 15][i >> 4] = __ldg(w + i);   // w[ch][tap]
+  for (int i = threadIdx.x; i < 96; i += PE_WARPS * 32) {
+    s.bias[i] = __ldg(bias + i);
+    s.g[i] = __ldg(g + i);
+    s.beta[i] = __ldg(beta + i);
   }
-  for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < ntok; tok += warps_total) {
-    const int tx = tok % 80, ty = (tok / 80) % 24, b = tok / 1920;
+  __syncthreads();
+  const uint32_t w_addr = smem_u32(&s.wT[0][0]), b_addr = smem_u32(&s.bias[0]);
+  float(*tile)[PE_PITCH] = s.tile[warp];
+  const int groups = ntok >> 5;                                   // ntok = B * 1920 is a multiple of 32
+  for (int grp = blockIdx.x * PE_WARPS + warp; grp < groups; grp += gridDim.x * PE_WARPS) {
+    const int tok = grp * 32 + lane;
+    const int b = tok / 1920, rem = tok - b * 1920, ty = rem / 80, tx = rem - ty * 80;
     const float* base = img + ((size_t)b * 96 + ty * 4) * 320 + tx * 4;
     float px[16];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(base + r * 320));
-      px[4 * r] = p.x; px[4 * r + 1] = p.y; px[4 * r + 2] = p.z; px[4 * r + 3] = p.w;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * 320));
+      px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w;
     }
-    float o[3];
+    uint64_t acc[48];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float a = br[c];
+    for (int c = 0; c < 24; ++c)
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(acc[2 * c]), "=l"(acc[2 * c + 1]) : "r"(b_addr + c * 16));
 #pragma unroll
-      for (int k = 0; k < 16; ++k) a = fmaf(px[k], wr[c][k], a);
-      o[c] = a;
+    for (int k = 0; k < 16; ++k) {
+      const uint64_t pk = pk2(px[k], px[k]);
+#pragma unroll
+      for (int c = 0; c < 24; ++c) {
+        uint64_t w0, w1;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(w_addr + (k * 96 + c * 4) * 4));
+        acc[2 * c] = fma2(pk, w0, acc[2 * c]);
+        acc[2 * c + 1] = fma2(pk, w1, acc[2 * c + 1]);
+      }
     }
-    const float mean = warp_sum(o[0] + o[1] + o[2]) * (1.0f / 96.0f);
-    const float d0 = o[0] - mean, d1 = o[1] - mean, d2 = o[2] - mean;
-    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.0f / 96.0f) + LN_EPS);
-    float* xo = x + (size_t)tok * 96;
-    xo[lane] = d0 * rstd * gr[0] + ber[0];
-    xo[lane + 32] = d1 * rstd * gr[1] + ber[1];
-    xo[lane + 64] = d2 * rstd * gr[2] + ber[2];
+    float o[96];
+#pragma unroll
+    for (int c = 0; c < 48; ++c) upk2(acc[c], o[2 * c], o[2 * c + 1]);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 96; ++c) sum += o[c];
+    const float mean = sum * (1.0f / 96.0f);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 96; ++c) { o[c] -= mean; sq = fmaf(o[c], o[c], sq); }
+    const float rstd = rsqrtf(sq * (1.0f / 96.0f) + LN_EPS);
+    __syncwarp();                                                   // the previous group has left the tile
+#pragma unroll
+    for (int c = 0; c < 24; ++c) {
+      const float4 gg = *reinterpret_cast<const float4*>(&s.g[4 * c]);
+      const float4 bb = *reinterpret_cast<const float4*>(&s.beta[4 * c]);
+      *reinterpret_cast<float4*>(&tile[lane][4 * c]) =
+          make_float4(fmaf(o[4 * c] * rstd, gg.x, bb.x), fmaf(o[4 * c + 1] * rstd, gg.y, bb.y),
+                      fmaf(o[4 * c + 2] * rstd, gg.z, bb.z), fmaf(o[4 * c + 3] * rstd, gg.w, bb.w));
+    }
+    __syncwarp();
+    float* xo = x + (size_t)grp * 32 * 96;
+#pragma unroll
+    for (int it = 0; it < 24; ++it) {
+      const int f = it * 128 + lane * 4, tk = f / 96, ch = f - tk * 96;
+      *reinterpret_cast<float4*>(xo + f) = *reinterpret_cast<const float4*>(&tile[tk][ch]);
+    }
   }
 }
 
@@ -382,9 +423,14 @@ int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin
 int patch_embed(cudaStream_t st, const float* images, int B, const float* w, const float* b, const float* g,
                 const float* beta, float* x) {
   const int ntok = B * 24 * 80;
-  int blocks = ceil_div(ntok, 8 * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  patch_embed_kernel<<<blocks, 256, 0, st>>>(images, ntok, w, b, g, beta, x);
+  static bool attr = false;
+  if (!attr) {
+    HM_CUDA(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PatchSmem)));
+    attr = true;
+  }
+  int blocks = ceil_div(ntok / 32, PE_WARPS);
+  if (blocks > 148 * 3) blocks = 148 * 3;
+  patch_embed_kernel<<<blocks, PE_WARPS * 32, sizeof(PatchSmem), st>>>(images, ntok, w, b, g, beta, x);
   HM_LAUNCHED();
   return 0;
 }
