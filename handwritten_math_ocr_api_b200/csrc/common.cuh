@@ -53,9 +53,33 @@ extern thread_local long g_launch_count;      // kernels launched by this librar
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch: the encoder is ~95 short kernels on one stream, and a plain launch only starts
+// once the previous grid has drained.  Kernels launched through launch_pdl() may start (block scheduling, shared
+// memory carve-out, barrier / TMEM set-up, loads of weights) while the previous kernel's last CTAs still run;
+// they call pdl_wait() before touching anything an earlier kernel wrote, and pdl_launch_dependents() at their
+// top so the same holds for their successor.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

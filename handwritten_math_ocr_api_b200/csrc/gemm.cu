@@ -296,6 +296,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -316,6 +317,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_kb = (p.K + BK - 1) / BK;
+  pdl_wait();              // A, the residual and the output buffers belong to earlier kernels up to here
 
   if (warp == 0) {
     if (lane == 0) {
@@ -456,7 +458,7 @@ int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* 
   p.mode = epi.ln_gamma != nullptr ? EPI_LN
            : (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-  gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  HM_CUDA(launch_pdl(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, p));
   HM_LAUNCHED();
   return 0;
 }

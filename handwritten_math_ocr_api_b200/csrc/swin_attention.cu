@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) window_attn_mma_kernel(const h1
   CtaShared& cs = *reinterpret_cast<CtaShared*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpTile& s = cs.w[warp];
+  pdl_launch_dependents();
   const int per_head = gridDim.x / heads;                    // CTAs working on one head
   if (per_head == 0 || (int)blockIdx.x >= per_head * heads) return;
   const int h = blockIdx.x % heads;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) window_attn_mma_kernel(const h1
     padv[m] = make_uint4(pack16(a.x, a.y), pack16(a.z, a.w), pack16(c4.x, c4.y), pack16(c4.z, c4.w));
   }
   __syncthreads();
+  pdl_wait();              // qkv comes from the previous kernel
 
   const uint32_t zero_addr = smem_u32(&cs.zero[0]);
   const uint32_t q_addr = smem_u32(&s.q[0][0]), k_addr = smem_u32(&s.k[0][0]), v_addr = smem_u32(&s.v[0][0]);
@@ -249,7 +251,8 @@ int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, con
   if (need < per_head) per_head = need;
   if (per_head < 1) per_head = 1;
   const int grid = per_head * heads;
-  window_attn_mma_kernel<<<grid, WARPS * 32, smem, st>>>(qkv, qkv_bias, rel_bias, B, H, W, C, heads, sh, sw, Hp, Wp, ctx);
+  HM_CUDA(launch_pdl(window_attn_mma_kernel, dim3(grid), dim3(WARPS * 32), (size_t)smem, st, qkv, qkv_bias, rel_bias, B, H, W, C,
+                     heads, sh, sw, Hp, Wp, ctx));
   HM_LAUNCHED();
   return 0;
 }

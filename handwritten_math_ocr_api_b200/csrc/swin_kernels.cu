@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) layernorm_c_kernel(const float* __restric
   constexpr bool PARAMS_IN_REGS = V <= 3;
   const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
+  pdl_launch_dependents();
   float4 gr[PARAMS_IN_REGS ? V : 1], br[PARAMS_IN_REGS ? V : 1];
   if (PARAMS_IN_REGS) {
 #pragma unroll
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) layernorm_c_kernel(const float* __restric
       br[i] = __ldg(reinterpret_cast<const float4*>(beta) + g + G * i);
     }
   }
+  pdl_wait();
   for (int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += warps_total * RPW) {
     const int row = row0 + sub;
     const bool ok = row < rows;
@@ -166,7 +168,7 @@ int launch_ln_c(cudaStream_t st, const float* x, int rows, int H, int W, const f
   constexpr int RPW = 32 / (C / (4 * V));
   int blocks = ceil_div(rows, 8 * RPW);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  layernorm_c_kernel<C, V, MERGE><<<blocks, 256, 0, st>>>(x, rows, H, W, gamma, beta, out16, out32);
+  HM_CUDA(launch_pdl(layernorm_c_kernel<C, V, MERGE>, dim3(blocks), dim3(256), 0, st, x, rows, H, W, gamma, beta, out16, out32));
   HM_LAUNCHED();
   return 0;
 }
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(PE_WARPS * 32, 3) patch_embed_kernel(const flo
   extern __shared__ __align__(16) uint8_t pe_raw[];
   PatchSmem& s = *reinterpret_cast<PatchSmem*>(pe_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 96 * 16; i += PE_WARPS * 32) s.wT[i & 15][i >> 4] = __ldg(w + i);   // w[ch][tap]
   for (int i = threadIdx.x; i < 96; i += PE_WARPS * 32) {
     s.bias[i] = __ldg(bias + i);
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(PE_WARPS * 32, 3) patch_embed_kernel(const flo
     s.beta[i] = __ldg(beta + i);
   }
   __syncthreads();
+  pdl_wait();
   const uint32_t w_addr = smem_u32(&s.wT[0][0]), b_addr = smem_u32(&s.bias[0]);
   float(*tile)[PE_PITCH] = s.tile[warp];
   const int groups = ntok >> 5;                                   // ntok = B * 1920 is a multiple of 32
@@ -430,7 +434,7 @@ int patch_embed(cudaStream_t st, const float* images, int B, const float* w, con
   }
   int blocks = ceil_div(ntok / 32, PE_WARPS);
   if (blocks > 148 * 3) blocks = 148 * 3;
-  patch_embed_kernel<<<blocks, PE_WARPS * 32, sizeof(PatchSmem), st>>>(images, ntok, w, b, g, beta, x);
+  HM_CUDA(launch_pdl(patch_embed_kernel, dim3(blocks), dim3(PE_WARPS * 32), sizeof(PatchSmem), st, images, ntok, w, b, g, beta, x));
   HM_LAUNCHED();
   return 0;
 }
