@@ -44,6 +44,7 @@ SIGNATURES = {
     "hmocr_patch_embed": (_i, [_p, _i, _p, _p, _p, _p, _p, _p]),
     "hmocr_patch_merge_ln": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "hmocr_window_attention": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "hmocr_self_attention": (_i, [_p, _i, _i, _i, _i, _p, _p]),
 }
 
 _lib = None

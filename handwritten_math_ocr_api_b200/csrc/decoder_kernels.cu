@@ -281,6 +281,7 @@ int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, 
 
 int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16, bool causal) {
   HM_CHECK(T <= 32 * MAXK, "attention: T=%d exceeds %d", T, 32 * MAXK);
+  if (!causal) return mha_full_mma(st, qkv16, B, T, nhead, ctx16);
   prefill_self_kernel<<<ceil_div(B * T * nhead, 8), 256, 0, st>>>(qkv16, B, T, nhead, causal ? 1 : 0, ctx16);
   HM_LAUNCHED();
   return 0;

@@ -1206,6 +1206,13 @@ HM_API int hmocr_patch_merge_ln(const float* x, int B, int H, int W, int C, cons
                         static_cast<h16*>(out_f16));
 }
 
+HM_API int hmocr_self_attention(const void* qkv, int B, int T, int nhead, int causal, void* ctx, void* stream) {
+  HM_CHECK(qkv != nullptr && ctx != nullptr, "null buffer");
+  HM_CHECK(B >= 1 && T >= 1 && nhead >= 1, "bad shape B=%d T=%d nhead=%d", B, T, nhead);
+  return mha_prefill_self(static_cast<cudaStream_t>(stream), static_cast<const h16*>(qkv), B, T, nhead,
+                          static_cast<h16*>(ctx), causal != 0);
+}
+
 HM_API int hmocr_window_attention(const void* qkv, const float* qkv_bias, const float* rel_bias, int B, int H, int W,
                                   int C, int heads, int shift, void* ctx, void* stream) {
   return window_attention(static_cast<cudaStream_t>(stream), static_cast<const h16*>(qkv), qkv_bias,

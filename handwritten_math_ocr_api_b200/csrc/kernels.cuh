@@ -32,6 +32,8 @@ int embed_tokens(cudaStream_t st, const int64_t* tok, int ld_tok, int B, int T, 
 //   self : q,k,v = columns [0,d),[d,2d),[2d,3d) of qkv16 (row pitch 3d), causal
 //   cross: q from q16 (pitch d); k,v from memkv (row (b*S+s), pitch ld_mem, column offsets koff/voff)
 int mha_prefill_self(cudaStream_t st, const h16* qkv16, int B, int T, int nhead, h16* ctx16, bool causal = true);
+// non-causal, T <= 256: tensor-core kernel (swin_attention.cu); used by mha_prefill_self(causal = false)
+int mha_full_mma(cudaStream_t st, const h16* qkv, int B, int T, int nhead, h16* ctx);
 int mha_prefill_cross(cudaStream_t st, const h16* q16, const h16* memkv, int ld_mem, int koff,
                       int voff, int B, int T, int S, int nhead, h16* ctx16);
 

@@ -62,10 +62,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
 __global__ void __launch_bounds__(WARPS * 32, 2) window_attn_mma_kernel(const h16* __restrict__ qkv,
                                                                         const float* __restrict__ qkv_bias,
                                                                         const float* __restrict__ rel_bias, int B, int H,
@@ -229,6 +225,125 @@ __global__ void __launch_bounds__(WARPS * 32, 2) window_attn_mma_kernel(const h1
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Full (non-causal) multi-head self-attention on tensor cores, head_dim 32, up to 256 keys: the
+// nn.TransformerEncoder of the ResNet-18 variant (/root/reference/src/model_res18trans.py:62-64, which attends
+// ACROSS the batch: "sequence" = the images of the batch, "batch" = the 10 feature columns).
+// One CTA = one (sequence b, head h): K and V of the head sit in shared memory (padded 80-byte rows), each
+// warp takes 16-query tiles and runs a flash-style online softmax over 64-key chunks; S = Q K^T and O = P V
+// on mma.sync with P re-packed from the S accumulators (same fragment algebra as the window kernel above).
+// ------------------------------------------------------------------------------------------------
+constexpr int FA_MAXT = 256, FA_WARPS = 8;
+struct FullAttnSmem {
+  h16 k[FA_MAXT][TP];
+  h16 v[FA_MAXT][TP];
+};
+
+__global__ void __launch_bounds__(FA_WARPS * 32) full_attn_mma_kernel(const h16* __restrict__ qkv, int T, int nhead,
+                                                                     h16* __restrict__ ctx) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  FullAttnSmem& s = *reinterpret_cast<FullAttnSmem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int b = blockIdx.x / nhead, h = blockIdx.x - b * nhead;
+  const int d = nhead * HD, pitch = 3 * d;
+  const h16* base = qkv + (size_t)b * T * pitch + h * HD;
+  const int Tp = (T + 63) & ~63;                               // keys are processed 64 at a time
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < Tp * 8; i += FA_WARPS * 32) {
+    const int j = i >> 3, m = (i >> 2) & 1, ch = i & 3;
+    h16* dst = (m == 0 ? &s.k[j][0] : &s.v[j][0]) + ch * 8;
+    if (j < T) {
+      const h16* src = base + (size_t)j * pitch + (m + 1) * d + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const float scale = 0.17677669529663687f * 1.4426950408889634f;     // 32^-0.5 * log2(e): softmax on ex2
+  const uint32_t k_lane = smem_u32(&s.k[lane & 7][((lane >> 3) & 1) * 8]);
+  const uint32_t v_lane = smem_u32(&s.v[lane & 15][0]);
+  for (int mt = warp; mt * 16 < T; mt += FA_WARPS) {
+    const int r0 = mt * 16 + g4, r1 = r0 + 8;
+    uint32_t aq[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const h16* q0 = base + (size_t)r0 * pitch + ks * 16 + 2 * t4;
+      const h16* q1 = base + (size_t)r1 * pitch + ks * 16 + 2 * t4;
+      aq[ks][0] = r0 < T ? __ldg(reinterpret_cast<const uint32_t*>(q0)) : 0u;
+      aq[ks][1] = r1 < T ? __ldg(reinterpret_cast<const uint32_t*>(q1)) : 0u;
+      aq[ks][2] = r0 < T ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 8)) : 0u;
+      aq[ks][3] = r1 < T ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 8)) : 0u;
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll 1
+    for (int kc = 0; kc < Tp; kc += 64) {
+      float sc[8][4];
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t bk[2];
+        const uint32_t ka = k_lane + (kc + nt * 8) * (TP * 2);
+        ldsm2(ka, bk);
+        mma16816(c, aq[0], bk);
+        ldsm2(ka + 32, bk);
+        mma16816(c, aq[1], bk);
+        const int c0 = kc + nt * 8 + 2 * t4;
+        sc[nt][0] = c0 < T ? c[0] * scale : -INFINITY;
+        sc[nt][1] = c0 + 1 < T ? c[1] * scale : -INFINITY;
+        sc[nt][2] = c0 < T ? c[2] * scale : -INFINITY;
+        sc[nt][3] = c0 + 1 < T ? c[3] * scale : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);      // finite: every chunk holds at least one real key
+      const float f0 = ex2_approx(m0 - n0), f1 = ex2_approx(m1 - n1);
+      m0 = n0; m1 = n1;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = ex2_approx(sc[nt][0] - n0), p1 = ex2_approx(sc[nt][1] - n0);
+        const float p2 = ex2_approx(sc[nt][2] - n1), p3 = ex2_approx(sc[nt][3] - n1);
+        sum0 += p0 + p1; sum1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2] = pack16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack16(p2, p3);
+      }
+      l0 = l0 * f0 + sum0; l1 = l1 * f1 + sum1;                  // per-lane partial sums; quad-reduced at the end
+#pragma unroll
+      for (int nt2 = 0; nt2 < 4; ++nt2) {
+        o[nt2][0] *= f0; o[nt2][1] *= f0; o[nt2][2] *= f1; o[nt2][3] *= f1;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t bv[2];
+          ldsm2_trans(v_lane + (kc + kk * 16) * (TP * 2) + nt2 * 16, bv);
+          mma16816(o[nt2], pa[kk], bv);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    h16* out0 = ctx + (size_t)(b * T + r0) * d + h * HD + 2 * t4;
+    h16* out1 = ctx + (size_t)(b * T + r1) * d + h * HD + 2 * t4;
+#pragma unroll
+    for (int nt2 = 0; nt2 < 4; ++nt2) {
+      if (r0 < T) *reinterpret_cast<uint32_t*>(out0 + nt2 * 8) = pack16(o[nt2][0] * inv0, o[nt2][1] * inv0);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(out1 + nt2 * 8) = pack16(o[nt2][2] * inv1, o[nt2][3] * inv1);
+    }
+  }
+}
+
 }  // namespace
 
 int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
@@ -253,6 +368,19 @@ int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, con
   const int grid = per_head * heads;
   HM_CUDA(launch_pdl(window_attn_mma_kernel, dim3(grid), dim3(WARPS * 32), (size_t)smem, st, qkv, qkv_bias, rel_bias, B, H, W, C,
                      heads, sh, sw, Hp, Wp, ctx));
+  HM_LAUNCHED();
+  return 0;
+}
+
+// qkv fp16 [B*T, 3*nhead*32] (row = b*T + t) -> ctx fp16 [B*T, nhead*32]; T <= 256
+int mha_full_mma(cudaStream_t st, const h16* qkv, int B, int T, int nhead, h16* ctx) {
+  HM_CHECK(T >= 1 && T <= FA_MAXT, "mha_full_mma: T=%d out of range", T);
+  static bool attr = false;
+  if (!attr) {
+    HM_CUDA(cudaFuncSetAttribute(full_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullAttnSmem)));
+    attr = true;
+  }
+  HM_CUDA(launch_pdl(full_attn_mma_kernel, dim3(B * nhead), dim3(FA_WARPS * 32), sizeof(FullAttnSmem), st, qkv, T, nhead, ctx));
   HM_LAUNCHED();
   return 0;
 }

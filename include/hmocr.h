@@ -155,6 +155,13 @@ int hmocr_patch_embed(const float* images_dev, int batch, const float* conv_w_de
 int hmocr_patch_merge_ln(const float* x_dev, int batch, int H, int W, int C, const float* gamma_dev,
                          const float* beta_dev, void* out_f16_dev, void* stream);
 
+/* torch.nn.MultiheadAttention core (head_dim 32, scale 32^-0.5) on a packed in-projection:
+ *   qkv fp16 [B*T, 3*nhead*32] (row = b*T + t; q | k | v) -> ctx fp16 [B*T, nhead*32] (input of out_proj).
+ * causal != 0: the teacher-forced decoder self-attention (generate_square_subsequent_mask,
+ * /root/reference/src/model_swin.py:75-77); causal == 0: nn.TransformerEncoderLayer.self_attn of the ResNet-18
+ * variant (/root/reference/src/model_res18trans.py:62-64), tensor-core kernel.  T <= 256. */
+int hmocr_self_attention(const void* qkv_dev, int B, int T, int nhead, int causal, void* ctx_f16_dev, void* stream);
+
 /* shifted_window_attention core (swin_transformer.py:151-214, 219-227) on a qkv buffer computed
  * for the real (un-padded, un-shifted) tokens:
  *   qkv fp16 [B*H*W, 3C] (bias included), qkv_bias f32 [3C] (value of padded tokens),

@@ -202,3 +202,23 @@ def _oracle_attention_from_qkv(qkv, dsd, bp, heads, shift):
     vf = valid.reshape(-1)
     res[:, src.reshape(-1)[vf], :] = ctx[:, vf, :]
     return res.reshape(B, H, W, C_)
+
+
+@pytest.mark.parametrize("B,T,causal", [(10, 256, 0), (10, 100, 0), (3, 1, 0), (2, 77, 0), (1, 64, 0), (4, 150, 1), (2, 33, 1)])
+def test_self_attention_matches_torch(B, T, causal):
+    """hmocr_self_attention (tensor-core kernel when not causal) vs fp32 softmax(q k^T / sqrt(32)) v."""
+    torch.manual_seed(B * 1000 + T)
+    nhead, hd = 8, 32
+    d = nhead * hd
+    qkv = (torch.randn(B * T, 3 * d, device="cuda") * 1.5).half()
+    ctx = torch.empty(B * T, d, device="cuda", dtype=torch.float16)
+    lib, L = _lib()
+    L.check(lib.hmocr_self_attention(P(qkv), B, T, nhead, causal, P(ctx), S()), "hmocr_self_attention")
+    torch.cuda.synchronize()
+    q, k, v = (x.float().view(B, T, nhead, hd).transpose(1, 2) for x in qkv.split(d, dim=1))
+    sc = (q @ k.transpose(-1, -2)) / hd ** 0.5
+    if causal:
+        sc = sc + torch.full((T, T), float("-inf"), device="cuda").triu(1)
+    ref = (sc.softmax(-1) @ v).transpose(1, 2).reshape(B * T, d)
+    err = (ctx.float() - ref).abs().max().item()
+    assert err < 4e-3, err
