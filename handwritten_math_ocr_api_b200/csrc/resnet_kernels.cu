@@ -10,39 +10,96 @@ namespace hmocr {
 namespace {
 
 // conv1: 7x7, stride 2, pad 3, 1 -> 64 channels (+ folded BN + ReLU).  images f32 [B,1,96,320] -> fp16 NHWC [B,48,160,64]
-// One thread = one output pixel x 8 channels; the 64 x 49 folded weights live in shared memory.
-__global__ void __launch_bounds__(256) conv7x7_kernel(const float* __restrict__ img, int B, const float* __restrict__ w,
-                                                      const float* __restrict__ bias, h16* __restrict__ out) {
-  __shared__ float ws[49][64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) ws[i % 49][i / 49] = w[i];       // w is [64][49]
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+// as an implicit GEMM on mma.sync: M = 16 consecutive output pixels of one row (a warp's work item), K = 49
+// taps padded to 64, N = 64 channels.  The folded weights sit in shared memory as the fp16 B operand
+// ([channel][tap], 144-byte rows: conflict-free ldmatrix); a warp copies the 7 x 37 input patch of its item into
+// a private fp32 buffer (zero padded at the image border) and builds the A fragments straight from it: tap k of
+// pixel p is patch[k / 7][2 p + k % 7], each lane's 16 tap offsets are fixed and live in registers.
+constexpr int C1_WARPS = 8, C1_WP = 72, C1_PP = 40;
+struct Conv1Smem {
+  h16 w[64][C1_WP];
+  float bias[64];
+  float patch[C1_WARPS][8][C1_PP];      // row 7 stays zero: where the padding taps 49..63 point
+};
+
+__global__ void __launch_bounds__(C1_WARPS * 32, 2) conv7x7_kernel(const float* __restrict__ img, int B,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, h16* __restrict__ out) {
+  __shared__ __align__(16) Conv1Smem s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  for (int i = threadIdx.x; i < 64 * 64; i += C1_WARPS * 32) {
+    const int ch = i >> 6, k = i & 63;
+    s.w[ch][k] = to_h16(k < 49 ? __ldg(w + ch * 49 + k) : 0.f);       // w is [64][49]
+  }
+  if (threadIdx.x < 64) s.bias[threadIdx.x] = __ldg(bias + threadIdx.x);
+  for (int i = lane; i < 8 * C1_PP; i += 32) (&s.patch[warp][0][0])[i] = 0.f;
   __syncthreads();
-  const size_t total = (size_t)B * 48 * 160 * 8;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cg = i & 7;
-    const size_t pix = i >> 3;
-    const int ox = pix % 160, oy = (pix / 160) % 48, b = pix / (160 * 48);
-    float acc[8];
+  float(*patch)[C1_PP] = s.patch[warp];
+  // fixed per lane: patch offsets (floats) of taps 16 ks + 2 t4 + {0, 1, 8, 9}, relative to column 2 p
+  int toff[4][4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = bs[cg * 8 + c];
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 16 * ks + 2 * t4 + (j & 1) + 8 * (j >> 1);
+      toff[ks][j] = k < 49 ? (k / 7) * C1_PP + (k % 7) : 7 * C1_PP;
+    }
+  const uint32_t w_lane = smem_u32(&s.w[lane & 7][(lane >> 3) * 8]);
+  const int items = B * 48 * 10;
+  for (int it = blockIdx.x * C1_WARPS + warp; it < items; it += gridDim.x * C1_WARPS) {
+    const int xt = it % 10, oy = (it / 10) % 48, b = it / 480;
     const float* ib = img + (size_t)b * 96 * 320;
-    for (int ky = 0; ky < 7; ++ky) {
-      const int iy = oy * 2 - 3 + ky;
-      if (iy < 0 || iy >= 96) continue;
+    const int ix0 = 32 * xt - 3, iy0 = 2 * oy - 3;
+    __syncwarp();                                   // the previous item's fragments have been read
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const int ix = ox * 2 - 3 + kx;
-        if (ix < 0 || ix >= 320) continue;
-        const float v = __ldg(ib + iy * 320 + ix);
-        const float* wr = &ws[ky * 7 + kx][cg * 8];
+    for (int r = 0; r < 7; ++r) {
+      const int iy = iy0 + r;
+      const bool rok = iy >= 0 && iy < 96;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+      for (int half = 0; half < 2; ++half) {
+        const int c = lane + 32 * half, ix = ix0 + c;
+        if (c < 37) patch[r][c] = (rok && ix >= 0 && ix < 320) ? __ldg(ib + iy * 320 + ix) : 0.f;
       }
     }
-    *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) =
-        make_uint4(pack16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)), pack16(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)),
-                   pack16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f)), pack16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f)));
+    __syncwarp();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    const float* p0 = &patch[0][2 * g4];            // pixel g4; pixel g4 + 8 is 16 columns further
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {                // k-steps 2 kp, 2 kp + 1: one ldmatrix.x4 per channel tile
+      uint32_t a[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ks = 2 * kp + h;
+        a[h][0] = pack16(p0[toff[ks][0]], p0[toff[ks][1]]);
+        a[h][1] = pack16(p0[toff[ks][0] + 16], p0[toff[ks][1] + 16]);
+        a[h][2] = pack16(p0[toff[ks][2]], p0[toff[ks][3]]);
+        a[h][3] = pack16(p0[toff[ks][2] + 16], p0[toff[ks][3] + 16]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t bw[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bw[0]), "=r"(bw[1]), "=r"(bw[2]), "=r"(bw[3])
+                     : "r"(w_lane + (nt * 8 * C1_WP + kp * 32) * 2));
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+              : "r"(a[h][0]), "r"(a[h][1]), "r"(a[h][2]), "r"(a[h][3]), "r"(bw[2 * h]), "r"(bw[2 * h + 1]));
+      }
+    }
+    h16* o0 = out + ((size_t)(b * 48 + oy) * 160 + xt * 16 + g4) * 64 + 2 * t4;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 bb = *reinterpret_cast<const float2*>(&s.bias[nt * 8 + 2 * t4]);
+      *reinterpret_cast<uint32_t*>(o0 + nt * 8) = pack16(fmaxf(acc[nt][0] + bb.x, 0.f), fmaxf(acc[nt][1] + bb.y, 0.f));
+      *reinterpret_cast<uint32_t*>(o0 + 8 * 64 + nt * 8) = pack16(fmaxf(acc[nt][2] + bb.x, 0.f), fmaxf(acc[nt][3] + bb.y, 0.f));
+    }
   }
 }
 
@@ -182,7 +239,9 @@ int preprocess_u8(cudaStream_t st, const uint8_t* in, size_t pixels, float* out)
   return 0;
 }
 int conv7x7_bn_relu(cudaStream_t st, const float* images, int B, const float* w, const float* bias, h16* out) {
-  conv7x7_kernel<<<blocks_for((size_t)B * 48 * 160 * 8), 256, 0, st>>>(images, B, w, bias, out);
+  int blocks = ceil_div(B * 48 * 10, C1_WARPS);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  conv7x7_kernel<<<blocks, C1_WARPS * 32, 0, st>>>(images, B, w, bias, out);
   HM_LAUNCHED();
   return 0;
 }
