@@ -99,6 +99,7 @@ struct hmocr_engine {
   int steps_per_launch = 16;
   int trace_step = -1;                // >= 0: record phase-boundary clocks of that decode step
   int dbg_flags = 0;                  // DecPersistParams::flags
+  int conv_impl = 0;                  // ResNet trunk: 0 = implicit GEMM (TMA patches), 1 = explicit im2col + GEMM
   int force_beam_kernel = 0;          // run beam = 1 through the beam-search kernel (A/B test against greedy)
 
   // scratch (grow-only); any reallocation invalidates the captured step graphs
@@ -360,6 +361,11 @@ int conv_gemm(hmocr_engine* e, cudaStream_t st, const h16* x16, int B, int H, in
               const Lin& w, h16* col, GemmEpilogue epi) {
   const int pad = (k == 3) ? 1 : 0;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  int tw, th, tn;
+  if (e->conv_impl == 0 && C % 64 == 0 && w.n % 64 == 0 && conv_tiling(Ho, Wo, &tw, &th, &tn)) {
+    epi.bias = w.b;
+    return gemm_conv_f16(st, x16, B, H, W, C, k, stride, pad, w.w, w.n, epi);       // implicit GEMM: TMA builds the patches
+  }
   HM_TRY(im2col(st, x16, B, H, W, C, k, stride, pad, col));
   return run_lin(st, col, k * k * C, B * Ho * Wo, w, epi);
 }
@@ -1041,6 +1047,9 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     e->steps_per_launch = value;
   } else if (n == "trace_step") {
     e->trace_step = value;
+  } else if (n == "conv_impl") {
+    HM_CHECK(value == 0 || value == 1, "conv_impl must be 0 (implicit GEMM) or 1 (im2col)");
+    e->conv_impl = value;
   } else if (n == "dbg_flags") {
     e->dbg_flags = value;
   } else if (n == "gemm_dbg") {

@@ -49,10 +49,27 @@ struct Cfg {
 
 enum EpiMode { EPI_GENERAL = 0, EPI_F16 = 1, EPI_LN = 2 };
 
+// Implicit-GEMM convolution (NHWC fp16 activations): an m-tile is a tw x th x tn box of output pixels
+// (w fastest, then h, then image), rows_valid = tw*th*tn <= 128 rows of the MMA tile; k-block kb is filter tap
+// kb / cin_blocks and input channels 64 * (kb % cin_blocks), fetched by ONE 4-D tiled TMA load at the tap's
+// offset - out-of-bounds coordinates are the zero padding, elementStrides are the convolution stride.
+struct ConvGeom {
+  int tw, th, tn, tiles_w, tiles_h, Ho, Wo, B, stride, pad, ksize, cin_blocks, rows_valid;
+};
+// output pixel (row of the NHWC output matrix) of row r of m-tile mi; -1 if the row is padding
+__device__ __forceinline__ int conv_pixel(const ConvGeom& g, int mi, int r) {
+  if (r >= g.rows_valid) return -1;
+  const int tile_w = mi % g.tiles_w, t2 = mi / g.tiles_w, tile_h = t2 % g.tiles_h, tile_n = t2 / g.tiles_h;
+  const int w = r % g.tw, r2 = r / g.tw, h = r2 % g.th, n = tile_n * g.tn + r2 / g.th;
+  if (n >= g.B) return -1;
+  return (n * g.Ho + tile_h * g.th + h) * g.Wo + tile_w * g.tw + w;
+}
+
 struct GemmParams {
   int M, N, K;
   int num_n_tiles, num_tiles;
   int mode;           // EpiMode, chosen on the host from the epilogue description
+  ConvGeom cg;        // CONV kernels only
   int dbg;            // timing experiments only: 1 = skip output stores, 2 = skip residual loads, 4 = skip the epilogue math
   GemmEpilogue epi;
 };
@@ -94,9 +111,10 @@ __device__ __forceinline__ void release_accumulator(bool last_chunk, uint64_t* r
 // opposite of one-row-per-thread: a warp instruction that covers whole rows.  So the packed rows go through a
 // 2 KB per-warp shared tile (16-byte pieces XOR-swizzled by row: conflict-free both ways) and leave as four
 // 16-byte stores per thread, each warp store covering 8 rows x 64 contiguous bytes.
-template <int BN, int ACT>
+template <int BN, int ACT, bool CONV>
 __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
-                                             int M, int n0, int c_first, int dbg, uint64_t* release_bar) {
+                                             int M, int n0, int c_first, int dbg, uint64_t* release_bar,
+                                             const ConvGeom& cg, int mi, int rq) {
   const int lane = threadIdx.x & 31;
   const uint32_t bias_addr = st_addr + 4096;
   const int srow = lane >> 2, sq = lane & 3;              // store layout: rows it*8 + srow, 16-byte piece sq
@@ -105,6 +123,11 @@ __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t tad
   h16* out = e.out_f16 + (size_t)(m_base + srow) * e.ld16 + n0 + sq * 8;
   const size_t out_step = (size_t)8 * e.ld16;
   const int rows_left = (dbg & 1) ? 0 : M - m_base - srow;       // row it*8 + srow exists iff it*8 < rows_left
+  int pix[4];                                                    // CONV: output pixel of row it*8 + srow, -1 if none
+  if (CONV) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) pix[it] = (dbg & 1) ? -1 : conv_pixel(cg, mi, rq + it * 8 + srow);
+  }
 #pragma unroll 1
   for (int c = c_first; c < BN / 32; c += 2) {
     const float b = e.bias != nullptr ? __ldg(e.bias + n0 + c * 32 + lane) : 0.0f;
@@ -139,7 +162,11 @@ __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t tad
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                    : "r"(rd_addr + it * 512));
-      if (it * 8 < rows_left) *reinterpret_cast<uint4*>(out + it * out_step + c * 32) = v;
+      if (CONV) {
+        if (pix[it] >= 0) *reinterpret_cast<uint4*>(e.out_f16 + (size_t)pix[it] * e.ld16 + n0 + sq * 8 + c * 32) = v;
+      } else {
+        if (it * 8 < rows_left) *reinterpret_cast<uint4*>(out + it * out_step + c * 32) = v;
+      }
     }
   }
 }
@@ -150,26 +177,37 @@ __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t tad
 // contiguous bytes (fp16 copy: x 64) instead of 32 scattered 16-byte pieces.  Bias, activation and residual are
 // applied in that second layout, where a lane owns the same 4 columns for all 32 rows (one bias load per
 // chunk).  The residual loads are issued before the TMEM load so their latency overlaps it.
-template <int BN, bool RES>
+template <int BN, bool RES, bool CONV>
 __device__ __forceinline__ void epilogue_general(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
-                                                 int M, int n0, int c_first, int dbg, uint64_t* release_bar) {
+                                                 int M, int n0, int c_first, int dbg, uint64_t* release_bar,
+                                                 const ConvGeom& cg, int mi, int rq) {
   const int lane = threadIdx.x & 31;
-  const int rr = lane >> 3, cg = lane & 7;            // second layout: row (it*4 + rr), columns 4*cg .. 4*cg+3
+  const int rr = lane >> 3, cg4 = lane & 7;            // second layout: row (it*4 + rr), columns 4*cg .. 4*cg+3
   const float lo_pre = e.act == 2 ? 0.0f : -INFINITY, lo_post = e.act == 3 ? 0.0f : -INFINITY;
   const int rows_left = M - m_base - rr;              // row it*4 + rr exists iff it*4 < rows_left
   const int rows_store = (dbg & 1) ? 0 : rows_left;
   const uint32_t wr_addr = st_addr + lane * 128, wr_sw = lane & 7;
-  const uint32_t rd_addr = st_addr + rr * 128;        // + it*512 + ((cg ^ ((it*4 + rr) & 7)) << 4)
+  const uint32_t rd_addr = st_addr + rr * 128;        // + it*512 + ((cg4 ^ ((it*4 + rr) & 7)) << 4)
+  int pix[8];                                         // CONV: output pixel of row it*4 + rr, -1 if none
+  if (CONV) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) pix[it] = conv_pixel(cg, mi, rq + it * 4 + rr);
+  }
 #pragma unroll 1
   for (int c = c_first; c < BN / 32; c += 2) {
-    const int col = n0 + c * 32 + cg * 4;
+    const int col = n0 + c * 32 + cg4 * 4;
     float4 res[8];
     if (RES) {
       const float* rp = e.residual + (size_t)(m_base + rr) * e.ldr + col;
 #pragma unroll
-      for (int it = 0; it < 8; ++it)
-        res[it] = (it * 4 < rows_left) ? __ldcs(reinterpret_cast<const float4*>(rp + (size_t)it * 4 * e.ldr))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 8; ++it) {
+        if (CONV)
+          res[it] = pix[it] >= 0 ? __ldcs(reinterpret_cast<const float4*>(e.residual + (size_t)pix[it] * e.ldr + col))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        else
+          res[it] = (it * 4 < rows_left) ? __ldcs(reinterpret_cast<const float4*>(rp + (size_t)it * 4 * e.ldr))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
@@ -190,13 +228,19 @@ __device__ __forceinline__ void epilogue_general(const GemmEpilogue& e, uint32_t
       float4 v;
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                    : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "r"(rd_addr + it * 512 + ((cg ^ ((it * 4 + rr) & 7)) << 4)));
+                   : "r"(rd_addr + it * 512 + ((cg4 ^ ((it * 4 + rr) & 7)) << 4)));
       v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
       if (e.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
       v.x = fmaxf(v.x, lo_pre); v.y = fmaxf(v.y, lo_pre); v.z = fmaxf(v.z, lo_pre); v.w = fmaxf(v.w, lo_pre);
       if (RES) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
       v.x = fmaxf(v.x, lo_post); v.y = fmaxf(v.y, lo_post); v.z = fmaxf(v.z, lo_post); v.w = fmaxf(v.w, lo_post);
-      if (it * 4 < rows_store) {
+      if (CONV) {
+        if (pix[it] >= 0 && !(dbg & 1)) {
+          if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(e.out_f32 + (size_t)pix[it] * e.ld32 + col) = v;
+          if (e.out_f16 != nullptr)
+            *reinterpret_cast<uint2*>(e.out_f16 + (size_t)pix[it] * e.ld16 + col) = make_uint2(pack16(v.x, v.y), pack16(v.z, v.w));
+        }
+      } else if (it * 4 < rows_store) {
         if (o32 != nullptr) *reinterpret_cast<float4*>(o32 + (size_t)it * 4 * e.ld32) = v;
         if (o16 != nullptr)
           *reinterpret_cast<uint2*>(o16 + (size_t)it * 4 * e.ld16) = make_uint2(pack16(v.x, v.y), pack16(v.z, v.w));
@@ -278,7 +322,7 @@ __device__ __forceinline__ void epilogue_ln(const GemmEpilogue& e, uint32_t tadd
   }
 }
 
-template <int BN>
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
@@ -326,11 +370,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int m0 = (t / p.num_n_tiles) * BM;
         const int n0 = (t % p.num_n_tiles) * BN;
+        int cw = 0, chh = 0, cn = 0;                   // CONV: input coordinates of the tile's first pixel at tap (0,0)
+        if (CONV) {
+          const int mi = t / p.num_n_tiles;
+          const int tile_w = mi % p.cg.tiles_w, t2 = mi / p.cg.tiles_w;
+          cw = tile_w * p.cg.tw * p.cg.stride - p.cg.pad;
+          chh = (t2 % p.cg.tiles_h) * p.cg.th * p.cg.stride - p.cg.pad;
+          cn = (t2 / p.cg.tiles_h) * p.cg.tn;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* st = smem + s * C::STAGE_BYTES;
-          tma_load_2d(st, &tmA, &full_bar[s], kb * BK, m0);
+          if (CONV) {
+            mbar_expect_tx(&full_bar[s], p.cg.rows_valid * (BK * 2) + C::B_BYTES);
+            const int tap = kb / p.cg.cin_blocks, cb = kb - tap * p.cg.cin_blocks;
+            const int kh = tap / p.cg.ksize, kw = tap - kh * p.cg.ksize;
+            tma_load_4d(st, &tmA, &full_bar[s], cb * BK, cw + kw, chh + kh, cn);
+          } else {
+            mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            tma_load_2d(st, &tmA, &full_bar[s], kb * BK, m0);
+          }
           tma_load_2d(st + C::A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
@@ -380,16 +439,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait_backoff(&tfull_bar[group], aph);
       tc_fence_after();
       const int mb = m0 + quarter * 32;
+      const int mi = t / p.num_n_tiles, rq = quarter * 32;
       if (p.mode == EPI_LN) {
         const int row = mb + lane;
         if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row < p.M, n0);   // row statistics: one thread per row
       } else if (p.mode == EPI_F16) {
-        if (p.epi.act == 1) epilogue_f16<BN, 1>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
-        else if (p.epi.act == 2) epilogue_f16<BN, 2>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
-        else epilogue_f16<BN, 0>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
+        if (p.epi.act == 1) epilogue_f16<BN, 1, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
+        else if (p.epi.act == 2) epilogue_f16<BN, 2, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
+        else epilogue_f16<BN, 0, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
       } else {
-        if (has_res) epilogue_general<BN, true>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
-        else epilogue_general<BN, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group]);
+        if (has_res) epilogue_general<BN, true, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
+        else epilogue_general<BN, false, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
       }
       if (p.mode == EPI_LN) {
         tc_fence_before();
@@ -458,12 +518,110 @@ int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* 
   p.mode = epi.ln_gamma != nullptr ? EPI_LN
            : (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-  HM_CUDA(launch_pdl(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, p));
+  HM_CUDA(launch_pdl(gemm_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, p));
+  HM_LAUNCHED();
+  return 0;
+}
+
+// NHWC fp16 activation [B, H, W, C] as a 4-D tensor (C, W, H, B); box = 64 channels x (tw, th, tn) output pixels
+// visited with the convolution stride.
+std::map<std::tuple<const void*, int, int, int, int, int, int, int, int>, CUtensorMap> g_maps4;
+int get_tensor_map_nhwc(const void* ptr, int B, int H, int W, int C, int tw, int th, int tn, int stride, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, B, H, W, C, tw, th, tn, stride);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps4.find(key);
+  if (it != g_maps4.end()) {
+    *out = it->second;
+    return 0;
+  }
+  alignas(64) CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (NHWC) failed (%d) B=%d H=%d W=%d C=%d box=%dx%dx%d stride=%d", (int)r,
+           B, H, W, C, tw, th, tn, stride);
+  if (g_maps4.size() > 1024) g_maps4.clear();
+  g_maps4[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN>
+int launch_conv(cudaStream_t stream, const CUtensorMap& tmA, const h16* Wt, int N, int K, const ConvGeom& cg, int m_tiles,
+                const GemmEpilogue& epi) {
+  using C = Cfg<BN>;
+  alignas(64) CUtensorMap tmB;
+  HM_TRY(get_tensor_map(Wt, N, K, K, BN, &tmB));
+  GemmParams p;
+  p.M = m_tiles * BM; p.N = N; p.K = K;
+  p.num_n_tiles = N / BN;
+  p.num_tiles = m_tiles * p.num_n_tiles;
+  p.epi = epi;
+  p.dbg = g_gemm_dbg;
+  p.mode = (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
+  p.cg = cg;
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  HM_CUDA(launch_pdl(gemm_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, p));
   HM_LAUNCHED();
   return 0;
 }
 
 }  // namespace
+
+bool conv_tiling(int Ho, int Wo, int* tw, int* th, int* tn) {
+  if (Ho * Wo <= BM) {                        // whole images per tile
+    *tw = Wo; *th = Ho; *tn = BM / (Ho * Wo);
+    if (*tn > 256) *tn = 256;
+    return (*tw) * (*th) * (*tn) * 4 >= BM * 3;
+  }
+  *tn = 1;
+  int best_tw = 0, best_th = 0;
+  for (int w = 1; w <= Wo && w <= BM; ++w) {  // the fullest tw x th box that tiles the image exactly
+    if (Wo % w != 0) continue;
+    for (int h = 1; h <= Ho && w * h <= BM; ++h) {
+      if (Ho % h != 0) continue;
+      if (w * h > best_tw * best_th) { best_tw = w; best_th = h; }
+    }
+  }
+  *tw = best_tw; *th = best_th;
+  return best_tw * best_th * 4 >= BM * 3 && best_tw <= 256 && best_th <= 256;
+}
+
+int gemm_conv_f16(cudaStream_t stream, const h16* x, int B, int H, int W, int Cin, int ksize, int stride, int pad,
+                  const h16* Wt, int N, const GemmEpilogue& epi) {
+  HM_TRY(gemm_init());
+  const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+  ConvGeom cg;
+  HM_CHECK(conv_tiling(Ho, Wo, &cg.tw, &cg.th, &cg.tn), "conv: no tile box for a %dx%d output", Ho, Wo);
+  HM_CHECK(Cin % BK == 0, "conv: input channels %d must be a multiple of %d", Cin, BK);
+  HM_CHECK(cg.tw * stride <= 256 && cg.th * stride <= 256, "conv: tile box too large for TMA");
+  HM_CHECK(epi.ln_gamma == nullptr, "conv: fused LayerNorm is not supported");
+  HM_CHECK(epi.out_f32 != nullptr || epi.out_f16 != nullptr, "conv: no output");
+  cg.tiles_w = Wo / cg.tw; cg.tiles_h = Ho / cg.th;
+  cg.Ho = Ho; cg.Wo = Wo; cg.B = B; cg.stride = stride; cg.pad = pad; cg.ksize = ksize;
+  cg.cin_blocks = Cin / BK; cg.rows_valid = cg.tw * cg.th * cg.tn;
+  const int m_tiles = cg.tiles_w * cg.tiles_h * ceil_div(B, cg.tn);
+  const int K = ksize * ksize * Cin;
+  alignas(64) CUtensorMap tmA;
+  HM_TRY(get_tensor_map_nhwc(x, B, H, W, Cin, cg.tw, cg.th, cg.tn, stride, &tmA));
+  int bn = 0;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    if (N % cands[i] != 0) continue;
+    bn = cands[i];
+    if (m_tiles * (N / cands[i]) >= g_num_sms) break;
+  }
+  HM_CHECK(bn != 0, "conv: output channels %d must be a multiple of 64", N);
+  switch (bn) {
+    case 64: return launch_conv<64>(stream, tmA, Wt, N, K, cg, m_tiles, epi);
+    case 128: return launch_conv<128>(stream, tmA, Wt, N, K, cg, m_tiles, epi);
+    default: return launch_conv<256>(stream, tmA, Wt, N, K, cg, m_tiles, epi);
+  }
+}
 
 void gemm_set_debug(int v) { g_gemm_dbg = v; }
 
@@ -482,11 +640,14 @@ int gemm_init() {
            prop.minor);
   g_num_sms = prop.multiProcessorCount;
   // set once, up front: nothing but launches may happen while a step graph is being captured
-  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
-  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<96>::SMEM_BYTES));
-  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
-  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<192>::SMEM_BYTES));
-  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<96>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<192>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return 0;
 }

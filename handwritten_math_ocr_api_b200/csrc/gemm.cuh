@@ -24,6 +24,13 @@ struct GemmEpilogue {
 int gemm_f16(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* W,
               int N, const GemmEpilogue& epi, int force_bn = 0);
 
+// Convolution as an implicit GEMM on the same kernel: x fp16 NHWC [B, H, W, Cin] (Cin % 64 == 0), Wt fp16
+// [N, ksize*ksize*Cin] with K ordered (kh, kw, c); the epilogue's row index is the NHWC output pixel.
+// conv_tiling() says whether the output plane can be cut into <=128-pixel boxes (else: explicit im2col + gemm_f16).
+bool conv_tiling(int Ho, int Wo, int* tw, int* th, int* tn);
+int gemm_conv_f16(cudaStream_t stream, const h16* x, int B, int H, int W, int Cin, int ksize, int stride, int pad,
+                  const h16* Wt, int N, const GemmEpilogue& epi);
+
 int gemm_init();
 void gemm_set_debug(int v);   // timing experiments only (see gemm.cu)   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
 

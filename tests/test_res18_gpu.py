@@ -103,3 +103,22 @@ def test_beam_search_runs_on_the_variant(rmodel, gold):
     tokens, steps, _, score = rmodel.generate(_imgs(gold).cuda(), max_len=20, beam_size=3, pos_table=pos)
     g_tok, _, g_lp = rmodel.generate(_imgs(gold).cuda(), max_len=20, return_logprobs=True, pos_table=pos)
     assert tokens.shape[0] == 4 and torch.isfinite(score).all()
+
+
+@pytest.mark.parametrize("batch", [1, 3, 4, 9])
+def test_implicit_gemm_convolutions_match_the_im2col_path(rmodel, gold, batch):
+    """conv_impl 0 (4-D TMA patches feeding the tcgen05 GEMM, zero padding = out-of-bounds fill, stride =
+    elementStrides) against conv_impl 1 (explicit im2col matrix + the same GEMM): same fp16 operands, fp32
+    accumulation in a different order only.  Batches that do not fill the last 4-image tile of layer4 included."""
+    from handwritten_math_ocr_api_b200.synthetic import synth_images
+    imgs = synth_images(batch, 77).cuda()
+    pos = torch.from_numpy(gold["pos_table"])
+    try:
+        rmodel.set_option("conv_impl", 1)
+        ref = rmodel.encoder(imgs, pos).clone()
+    finally:
+        rmodel.set_option("conv_impl", 0)
+    out = rmodel.encoder(imgs, pos)
+    err = (out - ref).abs().max().item()
+    print("implicit vs im2col max-abs:", err)
+    assert err < 2e-3
