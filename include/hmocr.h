@@ -66,7 +66,9 @@ int hmocr_finalize_weights(hmocr_engine* e);
  *   "decode_impl"       0 = persistent thread-block-cluster decode kernel (default)
  *                       1 = one captured CUDA graph of per-layer kernels per step (kept for A/B tests)
  *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16)
- *   "force_beam_kernel" 1 = run beam == 1 through the beam-search kernel (A/B test against greedy) */
+ *   "force_beam_kernel" 1 = run beam == 1 through the beam-search kernel (A/B test against greedy)
+ *   "conv_impl"         ResNet-18 variant: 0 = convolutions as implicit GEMMs, the patches built by 4-D TMA
+ *                       loads (default); 1 = explicit im2col matrix + GEMM (kept for A/B tests) */
 int hmocr_set_option(hmocr_engine* e, const char* name, int value);
 /* Developer aid: with option "trace_step" = t >= 0 the persistent decode kernel records clock64()
  * of (cluster 0, CTA 0, thread 0) at every phase boundary of decode step t; this copies the first
