@@ -222,3 +222,22 @@ def test_self_attention_matches_torch(B, T, causal):
     ref = (sc.softmax(-1) @ v).transpose(1, 2).reshape(B * T, d)
     err = (ctx.float() - ref).abs().max().item()
     assert err < 4e-3, err
+
+
+def test_gelu_epilogue_is_the_exact_erf_form_over_a_dense_grid():
+    """nn.GELU() (erf form, swin_transformer.py:444) through the GEMM epilogue with an identity weight: the
+    single-MUFU evaluation max(x,0) - |x| 2^q(|x|) stays within 1e-6 of x * Phi(x) on 16k points of [-9, 9]
+    (fp32 output path), and the packed FFMA2 path of the fp16-output epilogue within fp16 rounding."""
+    n = 64
+    x = torch.linspace(-9.0, 9.0, 256 * n, device="cuda").half().view(256, n)       # exactly representable inputs
+    w = torch.eye(n, device="cuda").half()
+    ref = torch.nn.functional.gelu(x.double()).float()
+    o32, _ = gemm(x, w, act=1, out_f32=True)
+    assert (o32 - ref).abs().max().item() < 1e-6
+    small = x.float().abs() < 1
+    rel = ((o32 - ref).abs() / ref.abs().clamp_min(1e-30))[small & (ref != 0)]
+    assert rel.max().item() < 2e-5
+    _, o16 = gemm(x, w, act=1, out_f32=False, out_f16=True)
+    assert torch.equal(o16, ref.half()) or (o16.float() - ref).abs().max().item() < 1e-3 * 9
+    ulp_off = (o16.view(torch.int16).int() - ref.half().view(torch.int16).int()).abs().max().item()
+    assert ulp_off <= 1, ulp_off
