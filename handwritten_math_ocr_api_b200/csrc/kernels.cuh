@@ -13,8 +13,6 @@ int patch_embed(cudaStream_t st, const float* images, int B, const float* w, con
                 const float* beta, float* x);
 int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
                      int H, int W, int C, int heads, int shift, h16* ctx);       // tensor-core (swin_attention.cu)
-int window_attention_fp32(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias,
-                          int B, int H, int W, int C, int heads, int shift, h16* ctx);   // CUDA-core reference
 
 // ---- decoder -------------------------------------------------------------------------------------
 struct DecodeState {      // device-resident control block of one generate call

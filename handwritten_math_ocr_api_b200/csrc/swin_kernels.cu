@@ -263,131 +263,6 @@ __global__ void __launch_bounds__(PE_WARPS * 32, 3) patch_embed_kernel(const flo
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused shifted-window attention core.                         swin_transformer.py:151-214,219-227
-//
-// One CTA = one 7x7 window of one image x 3 heads.  The cyclic shift, the zero padding, the window
-// partition and their inverses are index arithmetic on the un-shifted, un-padded qkv buffer:
-// rolled position (r,c) reads padded position ((r+sh)%Hp, (c+sw)%Wp); a padded position has
-// q = k = v = qkv.bias (the reference pads with zeros AFTER norm1, so its Linear output is the
-// bias); outputs of padded positions are never written (the reference crops them).
-// Thread = (head, query row): q in registers, K/V of the window in shared memory (fp32),
-// scores + relative-position bias + (-100) region mask, softmax and P.V all in registers.
-// ------------------------------------------------------------------------------------------
-constexpr int WS = 7, WN = 49, HD = 32, HC = 3;
-
-struct WinSmem {
-  float k[HC][WN][HD];
-  float v[HC][WN][HD];
-  float bias[HC][WN][WN];
-  int tok[WN];      // token row in the qkv buffer, -1 if padded
-  int region[WN];
-};
-
-__global__ void __launch_bounds__(HC * 64) window_attn_kernel(const h16* __restrict__ qkv,
-                                                              const float* __restrict__ qkv_bias,
-                                                              const float* __restrict__ rel_bias, int H, int W, int C,
-                                                              int sh, int sw, int Hp, int Wp,
-                                                              h16* __restrict__ ctx) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  WinSmem& s = *reinterpret_cast<WinSmem*>(smem_raw);
-  const int nww = Wp / WS;
-  const int win = blockIdx.x, b = blockIdx.y, h0 = blockIdx.z * HC;
-  const int wr = win / nww, wc = win % nww;
-  const int tid = threadIdx.x;
-
-  if (tid < WN) {
-    const int r = wr * WS + tid / WS, c = wc * WS + tid % WS;      // rolled, padded coordinates
-    const int pr = (r + sh) % Hp, pc = (c + sw) % Wp;              // padded coordinates before the roll
-    s.tok[tid] = (pr < H && pc < W) ? (b * H + pr) * W + pc : -1;
-    int reg = 0;
-    if (sh + sw > 0) {
-      // slices (0,-7),(-7,-s),(-s,None) written in order; s == 0 makes the last one cover everything
-      const int hb = (sh == 0) ? 2 : ((r >= Hp - WS) + (r >= Hp - sh));
-      const int wb = (sw == 0) ? 2 : ((c >= Wp - WS) + (c >= Wp - sw));
-      reg = hb * 3 + wb;
-    }
-    s.region[tid] = reg;
-  }
-  // relative position bias of these 3 heads -> smem (coalesced)
-  for (int i = tid; i < HC * WN * WN; i += blockDim.x) (&s.bias[0][0][0])[i] = __ldg(rel_bias + (size_t)h0 * WN * WN + i);
-  __syncthreads();
-  // K and V rows of the window: 16-byte chunks of 8 fp16
-  for (int i = tid; i < HC * WN * 4 * 2; i += blockDim.x) {
-    const int chunk = i & 3, kv = (i >> 2) & 1, p = (i >> 3) % WN, h = (i >> 3) / WN;
-    const int col = (1 + kv) * C + (h0 + h) * HD + chunk * 8;
-    float* dst = (kv ? &s.v[h][p][0] : &s.k[h][p][0]) + chunk * 8;
-    const int tok = s.tok[p];
-    if (tok >= 0) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + col));
-      float2 a = unpack16(u.x), bb = unpack16(u.y), cc = unpack16(u.z), d = unpack16(u.w);
-      dst[0] = a.x; dst[1] = a.y; dst[2] = bb.x; dst[3] = bb.y; dst[4] = cc.x; dst[5] = cc.y; dst[6] = d.x; dst[7] = d.y;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dst[e] = __ldg(qkv_bias + col + e);
-    }
-  }
-  __syncthreads();
-
-  const int h = tid >> 6, i = tid & 63;
-  if (i >= WN) return;
-  const int tok = s.tok[i];
-  if (tok < 0) return;                       // padded query: its output is cropped by the reference
-  const float scale = 0.17677669529663687f;  // 32^-0.5, applied to q (swin_transformer.py:188)
-  float q[HD];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + (h0 + h) * HD);
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-      const uint4 u = __ldg(qp + c4);
-      float2 a = unpack16(u.x), bb = unpack16(u.y), cc = unpack16(u.z), d = unpack16(u.w);
-      q[8 * c4 + 0] = a.x * scale; q[8 * c4 + 1] = a.y * scale; q[8 * c4 + 2] = bb.x * scale; q[8 * c4 + 3] = bb.y * scale;
-      q[8 * c4 + 4] = cc.x * scale; q[8 * c4 + 5] = cc.y * scale; q[8 * c4 + 6] = d.x * scale; q[8 * c4 + 7] = d.y * scale;
-    }
-  }
-  const int my_region = s.region[i];
-  const bool masked = (sh + sw) > 0;
-  float sc[WN];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < WN; ++j) {
-    const float4* kp = reinterpret_cast<const float4*>(&s.k[h][j][0]);
-    float a = 0.f;
-#pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-      const float4 kk = kp[d4];
-      a = fmaf(q[4 * d4], kk.x, a); a = fmaf(q[4 * d4 + 1], kk.y, a);
-      a = fmaf(q[4 * d4 + 2], kk.z, a); a = fmaf(q[4 * d4 + 3], kk.w, a);
-    }
-    a += s.bias[h][i][j];
-    if (masked && s.region[j] != my_region) a += -100.0f;
-    sc[j] = a;
-    mx = fmaxf(mx, a);
-  }
-  float denom = 0.f;
-  float acc[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-#pragma unroll
-  for (int j = 0; j < WN; ++j) {
-    const float p = __expf(sc[j] - mx);
-    denom += p;
-    const float4* vp = reinterpret_cast<const float4*>(&s.v[h][j][0]);
-#pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-      const float4 vv = vp[d4];
-      acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
-      acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
-    }
-  }
-  const float inv = 1.0f / denom;
-  uint4* op = reinterpret_cast<uint4*>(ctx + (size_t)tok * C + (h0 + h) * HD);
-#pragma unroll
-  for (int c4 = 0; c4 < 4; ++c4)
-    op[c4] = make_uint4(pack16(acc[8 * c4] * inv, acc[8 * c4 + 1] * inv), pack16(acc[8 * c4 + 2] * inv, acc[8 * c4 + 3] * inv),
-                        pack16(acc[8 * c4 + 4] * inv, acc[8 * c4 + 5] * inv), pack16(acc[8 * c4 + 6] * inv, acc[8 * c4 + 7] * inv));
-}
-
 }  // namespace
 
 int layernorm(cudaStream_t st, const float* x, int rows, int C, const float* gamma, const float* beta,
@@ -435,24 +310,6 @@ int patch_embed(cudaStream_t st, const float* images, int B, const float* w, con
   int blocks = ceil_div(ntok / 32, PE_WARPS);
   if (blocks > 148 * 3) blocks = 148 * 3;
   HM_CUDA(launch_pdl(patch_embed_kernel, dim3(blocks), dim3(PE_WARPS * 32), sizeof(PatchSmem), st, images, ntok, w, b, g, beta, x));
-  HM_LAUNCHED();
-  return 0;
-}
-
-// CUDA-core fp32 version (round-1 first path); kept as an independent implementation for A/B tests.
-int window_attention_fp32(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
-                     int H, int W, int C, int heads, int shift, h16* ctx) {
-  HM_CHECK(C == heads * HD, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
-  HM_CHECK(heads % HC == 0, "window_attention: heads=%d must be a multiple of %d", heads, HC);
-  const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;
-  const int sh = (Hp > WS) ? shift : 0, sw = (Wp > WS) ? shift : 0;   // swin_transformer.py:158-163
-  static bool attr = false;
-  if (!attr) {
-    HM_CUDA(cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WinSmem)));
-    attr = true;
-  }
-  dim3 grid((Hp / WS) * (Wp / WS), B, heads / HC);
-  window_attn_kernel<<<grid, HC * 64, sizeof(WinSmem), st>>>(qkv, qkv_bias, rel_bias, H, W, C, sh, sw, Hp, Wp, ctx);
   HM_LAUNCHED();
   return 0;
 }
