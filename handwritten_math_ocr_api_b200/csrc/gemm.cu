@@ -98,10 +98,10 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 // Epilogue warps hand their TMEM accumulator back as soon as its last chunk has been loaded into registers
 // (the bias/activation/store work of that chunk then overlaps the next main loop).  The __syncwarp doubles as
 // the "bias slot is written" fence of the fp16 path.
-__device__ __forceinline__ void release_accumulator(bool last_chunk, uint64_t* release_bar) {
+__device__ __forceinline__ void release_accumulator(bool last_chunk, uint32_t release_bar) {   // shared::cluster address
   tc_fence_before();
   __syncwarp();
-  if (last_chunk && (threadIdx.x & 31) == 0) mbar_arrive(release_bar);
+  if (last_chunk && (threadIdx.x & 31) == 0) mbar_arrive_cluster(release_bar);
 }
 
 // fp16-output epilogue (qkv, fc1 + GELU, linear1 + ReLU: no residual, no fp32 copy) of one 32-row x BN-column
@@ -113,7 +113,7 @@ __device__ __forceinline__ void release_accumulator(bool last_chunk, uint64_t* r
 // 16-byte stores per thread, each warp store covering 8 rows x 64 contiguous bytes.
 template <int BN, int ACT, bool CONV>
 __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
-                                             int M, int n0, int c_first, int dbg, uint64_t* release_bar,
+                                             int M, int n0, int c_first, int dbg, uint32_t release_bar,
                                              const ConvGeom& cg, int mi, int rq) {
   const int lane = threadIdx.x & 31;
   const uint32_t bias_addr = st_addr + 4096;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void epilogue_f16(const GemmEpilogue& e, uint32_t tad
 // chunk).  The residual loads are issued before the TMEM load so their latency overlaps it.
 template <int BN, bool RES, bool CONV>
 __device__ __forceinline__ void epilogue_general(const GemmEpilogue& e, uint32_t taddr, uint32_t st_addr, int m_base,
-                                                 int M, int n0, int c_first, int dbg, uint64_t* release_bar,
+                                                 int M, int n0, int c_first, int dbg, uint32_t release_bar,
                                                  const ConvGeom& cg, int mi, int rq) {
   const int lane = threadIdx.x & 31;
   const int rr = lane >> 3, cg4 = lane & 7;            // second layout: row (it*4 + rr), columns 4*cg .. 4*cg+3
@@ -444,12 +444,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row = mb + lane;
         if (half == 0) epilogue_ln<BN>(p.epi, taddr, row, row < p.M, n0);   // row statistics: one thread per row
       } else if (p.mode == EPI_F16) {
-        if (p.epi.act == 1) epilogue_f16<BN, 1, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
-        else if (p.epi.act == 2) epilogue_f16<BN, 2, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
-        else epilogue_f16<BN, 0, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
+        if (p.epi.act == 1) epilogue_f16<BN, 1, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, smem_u32(&tempty_bar[group]), p.cg, mi, rq);
+        else if (p.epi.act == 2) epilogue_f16<BN, 2, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, smem_u32(&tempty_bar[group]), p.cg, mi, rq);
+        else epilogue_f16<BN, 0, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, smem_u32(&tempty_bar[group]), p.cg, mi, rq);
       } else {
-        if (has_res) epilogue_general<BN, true, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
-        else epilogue_general<BN, false, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, &tempty_bar[group], p.cg, mi, rq);
+        if (has_res) epilogue_general<BN, true, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, smem_u32(&tempty_bar[group]), p.cg, mi, rq);
+        else epilogue_general<BN, false, CONV>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, smem_u32(&tempty_bar[group]), p.cg, mi, rq);
       }
       if (p.mode == EPI_LN) {
         tc_fence_before();
@@ -464,6 +464,155 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the K-heavy shapes (Swin stages 3/4): their main loop is bound by the
+// L2 -> SM operand traffic, not by the tensor pipe.  Two CTAs of a cluster (one TPC) share a 256 x BN tile: each
+// loads ITS 128 rows of A and HALF of the W tile (BN/2 rows) per k-block - (128 + BN/2) x 128 B instead of
+// (128 + BN) x 128 B per 128 output rows - and the leader CTA's elected thread issues one M = 256 MMA that reads
+// both CTAs' shared memory and writes both CTAs' TMEM.  Protocol: "full" barriers live in the leader and count
+// the TMA bytes of both CTAs (the peer's loads name the leader's barrier); tcgen05.commit multicasts the
+// "slot free" and "accumulator ready" arrivals to both CTAs; the peer's epilogue warps release the accumulator
+// with a remote arrive on the leader's barrier.  Epilogues, groups and staging are those of the 1-CTA kernel.
+template <int BN>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int STAGES_RAW = (156 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_STAGE_BYTES;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const GemmParams p) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cta_rank_in_cluster();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);              // used in the leader only
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * GROUP_WARPS);   // leader only: the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_barrier();                            // both CTAs' barriers exist before any remote arrive / TMA completion
+  if (warp == 1) tmem_alloc2(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();                            // both allocations done: the leader's MMA writes the peer's TMEM too
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = (p.K + BK - 1) / BK;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = pair; t < p.num_tiles; t += npairs) {
+        const int m0 = (t / p.num_n_tiles) * (2 * BM) + rank * BM;
+        const int n0 = (t % p.num_n_tiles) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+          uint8_t* st = smem + s * C::STAGE_BYTES;
+          tma2_load_2d(st, &tmA, &full_bar[s], kb * BK, m0);
+          tma2_load_2d(st + C::A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);   // F16 in, F32 out, M = 256
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = pair; t < p.num_tiles; t += npairs, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait_backoff(&tempty_bar[a], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t bbase = abase + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma2_f16(d_tmem, make_smem_desc(abase + k * 32), make_smem_desc(bbase + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma2_commit(&empty_bar[s]);
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma2_commit(&tfull_bar[a]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int group = ew >> 3;
+    const int half = (ew >> 2) & 1;
+    const uint32_t st_addr = epi_stage + ew * EPI_WARP_BYTES;
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + group * BN;
+    const bool has_res = p.epi.residual != nullptr && !(p.dbg & 2);
+    const uint32_t release = smem_u32(&tempty_bar[group]) & PEER_BIT_MASK;      // the leader's barrier
+    int it = group;
+    for (int t = pair + group * npairs; t < p.num_tiles; t += 2 * npairs, it += 2) {
+      const uint32_t aph = (it >> 1) & 1;
+      const int m0 = (t / p.num_n_tiles) * (2 * BM) + rank * BM;
+      const int n0 = (t % p.num_n_tiles) * BN;
+      mbar_wait_backoff(&tfull_bar[group], aph);
+      tc_fence_after();
+      const int mb = m0 + quarter * 32;
+      if (p.mode == EPI_F16) {
+        if (p.epi.act == 1) epilogue_f16<BN, 1, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, release, p.cg, 0, 0);
+        else if (p.epi.act == 2) epilogue_f16<BN, 2, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, release, p.cg, 0, 0);
+        else epilogue_f16<BN, 0, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, release, p.cg, 0, 0);
+      } else {
+        if (has_res) epilogue_general<BN, true, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, release, p.cg, 0, 0);
+        else epilogue_general<BN, false, false>(p.epi, taddr, st_addr, mb, p.M, n0, half, p.dbg, release, p.cg, 0, 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();                            // the peer may still be reading operands / TMEM this CTA's MMA touches
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc2(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -570,6 +719,39 @@ int launch_conv(cudaStream_t stream, const CUtensorMap& tmA, const h16* Wt, int 
   return 0;
 }
 
+template <int BN>
+int launch2(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* W, int N, const GemmEpilogue& epi) {
+  using C = Cfg2<BN>;
+  alignas(64) CUtensorMap tmA, tmB;
+  HM_TRY(get_tensor_map(A, M, K, lda, BM, &tmA));
+  HM_TRY(get_tensor_map(W, N, K, K, BN / 2, &tmB));
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_n_tiles = N / BN;
+  p.num_tiles = ceil_div(M, 2 * BM) * p.num_n_tiles;
+  p.epi = epi;
+  p.dbg = g_gemm_dbg;
+  p.mode = (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
+  p.cg = ConvGeom{};
+  int pairs = g_num_sms / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  HM_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel<BN>, tmA, tmB, p));
+  HM_LAUNCHED();
+  return 0;
+}
+
 }  // namespace
 
 bool conv_tiling(int Ho, int Wo, int* tw, int* th, int* tn) {
@@ -645,6 +827,8 @@ int gemm_init() {
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<192>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<192>::SMEM_BYTES));
+  HM_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
@@ -682,6 +866,15 @@ int gemm_f16(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16
     }
     if (bn == 0) bn = smallest;
     HM_CHECK(bn != 0, "gemm: N=%d is not a multiple of 64 or 96", N);
+  }
+  // K-heavy shapes (fc2 of Swin stages 3/4, the last patch-merging reduction): the CTA-pair kernel's halved W-tile
+  // traffic is worth 8-15 % there (profiles/README.md); everything else stays on the 1-CTA kernel
+  if (force_bn == 0 && epi.ln_gamma == nullptr && K >= 1024 && N % 192 == 0 && M >= 4 * BM)
+    return launch2<192>(stream, A, lda, M, K, W, N, epi);
+  if (force_bn == 2192 || force_bn == 2256) {            // CTA-pair kernel, explicit (tests / timing)
+    bn = force_bn - 2000;
+    HM_CHECK(N % bn == 0 && epi.ln_gamma == nullptr, "gemm: pair kernel needs N %% %d == 0 and no fused LayerNorm", bn);
+    return bn == 192 ? launch2<192>(stream, A, lda, M, K, W, N, epi) : launch2<256>(stream, A, lda, M, K, W, N, epi);
   }
   HM_CHECK(N % bn == 0, "gemm: N=%d not divisible by tile width %d", N, bn);
   switch (bn) {

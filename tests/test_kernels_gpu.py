@@ -241,3 +241,24 @@ def test_gelu_epilogue_is_the_exact_erf_form_over_a_dense_grid():
     assert torch.equal(o16, ref.half()) or (o16.float() - ref).abs().max().item() < 1e-3 * 9
     ulp_off = (o16.view(torch.int16).int() - ref.half().view(torch.int16).int()).abs().max().item()
     assert ulp_off <= 1, ulp_off
+
+
+@pytest.mark.parametrize("M,K,N,fb", [(256, 64, 192, 2192), (300, 384, 1152, 2192), (1024, 1536, 384, 2192),
+                                      (768, 768, 768, 2256), (515, 384, 1536, 2256), (7680, 3072, 768, 2192)])
+def test_cta_pair_gemm_is_bit_identical_to_the_single_cta_kernel(M, K, N, fb):
+    """cta_group::2 kernel (256-row tiles shared by two CTAs; force_bn 2192 / 2256 select it explicitly, K >= 1024
+    shapes get it automatically) against the 1-CTA kernel: same MMA order along K, so the same bits - with the
+    GELU fp16 epilogue and with the fp32 residual epilogue, ragged M included."""
+    torch.manual_seed(M + K + N)
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
+    b = torch.randn(N, device="cuda")
+    r = torch.randn(M, N, device="cuda")
+    one = 192 if fb == 2192 else 256
+    _, p16 = gemm(a, w, bias=b, act=1, out_f32=False, out_f16=True, force_bn=fb)
+    _, s16 = gemm(a, w, bias=b, act=1, out_f32=False, out_f16=True, force_bn=one)
+    assert torch.equal(p16, s16)
+    p32, _ = gemm(a, w, bias=b, residual=r, force_bn=fb)
+    s32, _ = gemm(a, w, bias=b, residual=r, force_bn=one)
+    assert torch.equal(p32, s32)
+    assert (p32 - gemm_ref(a, w, bias=b, residual=r)).abs().max().item() < 2e-2
