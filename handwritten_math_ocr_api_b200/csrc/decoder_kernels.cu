@@ -261,6 +261,34 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, size_t n, h16* 
     dst[i] = to_h16(src[i]);
 }
 
+// ---- detokenise / pack ---------------------------------------------------------------------------------
+// What src/inference.py:29-40 does per sequence in Python (skip sos and pad wherever they occur, stop at the first
+// eos) as one warp per row: the ids that survive are written, in order, to packed[row, 0..len) and their count to
+// lengths[row]; the host then does ONE join per sequence instead of B x T dictionary look-ups behind .item() syncs.
+__global__ void __launch_bounds__(256) pack_tokens_kernel(const int64_t* __restrict__ tok, int rows, int ld_tok, int sos,
+                                                          int eos, int pad, int32_t* __restrict__ lengths,
+                                                          int32_t* __restrict__ packed) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t* row = tok + (size_t)r * ld_tok;
+  int32_t* out = packed + (size_t)r * ld_tok;
+  int n = 0;
+  for (int base = 0; base < ld_tok; base += 32) {
+    const int i = base + lane;
+    const long long id = i < ld_tok ? row[i] : (long long)eos;          // past the end behaves like eos
+    const unsigned is_eos = __ballot_sync(0xffffffffu, id == eos);
+    const int stop = is_eos ? __ffs(is_eos) - 1 : 32;                   // first eos of this chunk
+    const bool keep = lane < stop && id != sos && id != pad;
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[n + __popc(km & ((1u << lane) - 1u))] = (int32_t)id;
+    n += __popc(km);
+    if (is_eos) break;
+  }
+  for (int i = n + lane; i < ld_tok; i += 32) out[i] = pad;
+  if (lane == 0) lengths[r] = n;
+}
+
 inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   if (g > 148 * 16) g = 148 * 16;
@@ -352,6 +380,13 @@ int copy_logits(cudaStream_t st, const float* src, int ld, int rows, int n_valid
 
 int f32_to_f16(cudaStream_t st, const float* src, size_t n, h16* dst) {
   f32_to_f16_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, dst);
+  HM_LAUNCHED();
+  return 0;
+}
+
+int pack_tokens(cudaStream_t st, const int64_t* tokens, int rows, int ld_tok, int sos, int eos, int pad, int32_t* lengths,
+                int32_t* packed) {
+  pack_tokens_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(tokens, rows, ld_tok, sos, eos, pad, lengths, packed);
   HM_LAUNCHED();
   return 0;
 }

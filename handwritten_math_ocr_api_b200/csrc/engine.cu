@@ -1137,6 +1137,15 @@ HM_API int hmocr_generate_host(hmocr_engine* e, const float* images_host, int B,
   return 0;
 }
 
+HM_API int hmocr_pack_tokens(hmocr_engine* e, const int64_t* tokens_dev, int rows, int ld_tok, int32_t* lengths_dev,
+                             int32_t* packed_dev, void* stream) {
+  HM_CHECK(e != nullptr && tokens_dev != nullptr && lengths_dev != nullptr && packed_dev != nullptr, "hmocr_pack_tokens: null argument");
+  HM_CHECK(rows >= 1 && ld_tok >= 1, "hmocr_pack_tokens: bad shape rows=%d ld=%d", rows, ld_tok);
+  HM_CUDA(cudaSetDevice(e->device));
+  return pack_tokens(static_cast<cudaStream_t>(stream), tokens_dev, rows, ld_tok, e->cfg.sos_id, e->cfg.eos_id, e->cfg.pad_id,
+                     lengths_dev, packed_dev);
+}
+
 HM_API int hmocr_preprocess_u8(hmocr_engine* e, const uint8_t* images_u8_dev, int B, float* images_dev, void* stream) {
   HM_CHECK(e != nullptr && images_u8_dev != nullptr && images_dev != nullptr && B >= 1, "hmocr_preprocess_u8: bad argument");
   HM_CUDA(cudaSetDevice(e->device));

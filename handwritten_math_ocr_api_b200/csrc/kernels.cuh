@@ -49,6 +49,8 @@ int greedy_select(cudaStream_t st, DecodeState* state, const float* logits, int 
                   int64_t* tokens, int ld_tok, float* logprob, int max_len, int eos, uint8_t* finished,
                   const float* emb, const float* pos, int d, int max_pos, float* x32, h16* x16);
 int advance_step(cudaStream_t st, DecodeState* state);
+int pack_tokens(cudaStream_t st, const int64_t* tokens, int rows, int ld_tok, int sos, int eos, int pad, int32_t* lengths,
+                int32_t* packed);
 int init_decode(cudaStream_t st, DecodeState* state, int64_t* tokens, int ld_tok, int rows, int sos, int pad,
                 uint8_t* finished, float* logprob, int max_len);
 // after the loop: columns past steps_executed -> pad / 0, steps -> int32 out

@@ -28,6 +28,11 @@ def ids_to_strings(sequences, idx2char: Dict[int, str], config=_default_config) 
     return results
 
 
+def packed_to_strings(packed, lengths, idx2char: Dict[int, str]) -> List[str]:
+    """Strings from the device-side detokeniser (``model.pack_tokens``): one join per sequence."""
+    return [' '.join(idx2char[i] for i in row[:n]) for row, n in zip(packed, lengths)]
+
+
 def predict(images, model, vocab, idx2char, device=None, beam_size=3, config=_default_config, use_beam=False):
     """``predict(images, model, vocab, idx2char, device, beam_size=3)`` (src/inference.py:7).
 
@@ -39,6 +44,8 @@ def predict(images, model, vocab, idx2char, device=None, beam_size=3, config=_de
         raise RuntimeError("the B200 engine has no CPU path (device must be 'cuda')")
     if vocab[config.sos_token] != model.sos_id or vocab[config.eos_token] != model.eos_id:
         raise ValueError("vocab special-token ids differ from the ids the engine was built with")
+    if vocab[config.pad_token] != model.pad_id:
+        raise ValueError("vocab pad id differs from the id the engine was built with")
     out = model.generate(images, max_len=config.max_seq_len, beam_size=beam_size if use_beam else 1)
-    sequences = out[0].cpu().tolist()
-    return ids_to_strings(sequences, idx2char, config)
+    packed, lengths = model.pack_tokens(out[0])            # skip sos / pad, stop at eos: on the device
+    return packed_to_strings(packed.cpu().tolist(), lengths.cpu().tolist(), idx2char)

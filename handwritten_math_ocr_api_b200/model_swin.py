@@ -292,6 +292,20 @@ class FormulaRecognitionModel:
             return tokens[:, : n + 1], n, out_lp, score
         return tokens[:, : n + 1], n, out_lp
 
+    @torch.no_grad()
+    def pack_tokens(self, tokens: torch.Tensor):
+        """Detokenise on the device (the per-id Python loop of /root/reference/src/inference.py:29-40): drops sos /
+        pad ids, stops at the first eos.  ``tokens`` int64 ``[B, L]`` (CUDA) -> ``(packed int32 [B, L], lengths int32
+        [B])``, both on the device; row ``b`` keeps ``packed[b, :lengths[b]]``."""
+        t = tokens.to(device=self.device, dtype=torch.int64).contiguous()
+        B, L = t.shape
+        packed = torch.empty(B, L, dtype=torch.int32, device=self.device)
+        lengths = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._eng.lib.hmocr_pack_tokens(self._handle(), _ptr(t), B, L, _ptr(lengths), _ptr(packed), _stream()),
+                       "hmocr_pack_tokens")
+        return packed, lengths
+
     def set_option(self, name: str, value: int) -> None:
         """Engine options of ``hmocr_set_option`` (``decode_impl``, ``steps_per_launch``)."""
         _lib.check(self._eng.lib.hmocr_set_option(self._eng.handle, name.encode(), int(value)), "hmocr_set_option")

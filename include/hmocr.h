@@ -119,6 +119,13 @@ int hmocr_generate_host(hmocr_engine* e, const float* images_host, int batch, in
                         int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
                         void* stream);
 
+/* Detokenise on the device (the Python loop of /root/reference/src/inference.py:29-40): for every row of
+ * tokens int64 [rows, ld_tok] drop sos and pad ids wherever they occur, stop at the first eos, and write the
+ * surviving ids in order to packed int32 [rows, ld_tok] (tail filled with pad) and their count to lengths int32 [rows].
+ * The host then needs one D2H copy and one join per sequence. */
+int hmocr_pack_tokens(hmocr_engine* e, const int64_t* tokens_dev, int rows, int ld_tok, int32_t* lengths_dev,
+                      int32_t* packed_dev, void* stream);
+
 /* The tail of the reference's preprocessing on the device: ToTensor + Normalize(0.5, 0.5)
  * (/root/reference/app/src/preprocess.py:7-12, src/predict.py:36-41) of grayscale uint8 images that are already
  * 96 x 320: images_u8_dev uint8 [B,96,320] -> images_dev f32 [B,1,96,320] = (u/255 - 0.5)/0.5, bit-identical to

@@ -402,3 +402,48 @@ def test_device_preprocessing_is_bit_identical_to_the_reference_transform(model)
     ref = torch.stack([norm(transforms.functional.to_tensor(img.numpy()[:, :, None])) for img in u8])
     assert got.shape == ref.shape == (3, 1, 96, 320) and torch.equal(got, ref)
     assert torch.equal(synth_images(3, seed=1234)[1:], got[1:])       # = the float images the benchmark feeds
+
+
+def test_device_detokeniser_matches_the_reference_rule(model, cfg):
+    """hmocr_pack_tokens against the Python loop of /root/reference/src/inference.py:29-40 (ids_to_strings) on token
+    matrices with eos at every kind of position, sos / pad ids in the middle, rows without eos, and ragged widths."""
+    from handwritten_math_ocr_api_b200.inference import ids_to_strings, packed_to_strings
+    g = torch.Generator().manual_seed(7)
+    idx2char = {i: f"t{i}" for i in range(cfg.vocab_size)}
+    idx2char[model.pad_id], idx2char[model.sos_id], idx2char[model.eos_id] = "<pad>", "<sos>", "<eos>"
+    for B, L in [(1, 1), (3, 31), (8, 32), (5, 33), (64, 151), (7, 257)]:
+        t = torch.randint(3, cfg.vocab_size, (B, L), generator=g)
+        t[:, 0] = model.sos_id
+        for b in range(B):
+            kind = b % 5
+            if kind == 0 and L > 1:
+                t[b, int(torch.randint(1, L, (1,), generator=g))] = model.eos_id          # one eos somewhere
+            elif kind == 1 and L > 3:
+                pos = torch.randint(1, L, (3,), generator=g)
+                t[b, pos[0]] = model.pad_id; t[b, pos[1]] = model.sos_id; t[b, pos[2]] = model.eos_id
+            elif kind == 2:
+                t[b, L - 1] = model.eos_id                                                # eos in the last column
+            elif kind == 3 and L > 2:
+                t[b, 1] = model.eos_id; t[b, 2:] = model.pad_id                           # empty formula
+            # kind 4: no eos at all
+        packed, lengths = model.pack_tokens(t.cuda())
+        got = packed_to_strings(packed.cpu().tolist(), lengths.cpu().tolist(), idx2char)
+        want = ids_to_strings(t.tolist(), idx2char)
+        assert got == want, (B, L)
+        pk, ln = packed.cpu(), lengths.cpu()
+        for b in range(B):
+            assert (pk[b, int(ln[b]):] == model.pad_id).all()
+
+
+def test_inference_predict_strings_match_the_reference_tokens(model, cfg, golden_src):
+    """inference.predict (one generate call + device detokeniser) gives the strings the reference's ys decode to."""
+    from handwritten_math_ocr_api_b200 import inference
+    idx2char = {i: f"t{i}" for i in range(cfg.vocab_size)}
+    idx2char[model.pad_id], idx2char[model.sos_id], idx2char[model.eos_id] = "<pad>", "<sos>", "<eos>"
+    vocab = {v: k for k, v in idx2char.items()}
+    imgs = _images(golden_src).cuda()
+    got = inference.predict(imgs, model, vocab, idx2char, "cuda")
+    tokens, _, _ = model.generate(imgs)
+    assert got == inference.ids_to_strings(tokens.cpu().tolist(), idx2char)
+    ref = inference.ids_to_strings(golden_src["greedy_ys"].tolist(), idx2char)
+    assert sum(a == b for a, b in zip(got, ref)) >= 3       # near-tie divergences are checked in the token test
