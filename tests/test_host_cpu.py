@@ -69,3 +69,18 @@ def test_confidence_bookkeeping_matches_reference(cfg, sd, golden_app, golden_sr
     formula, conf = _finish(ys[0, 1:].tolist(), lp[0].tolist(), cfg.eos, idx2char)
     assert formula == str(golden_app["formulas"][1])
     assert abs(conf - float(golden_app["confidences"][1])) < 1e-4
+
+
+def test_evaluation_metrics_follow_the_reference_formula():
+    """evaluate.calculate_metrics = src/test_model.py:47-58 (SequenceMatcher ratio over characters, exact match)."""
+    from difflib import SequenceMatcher
+    from handwritten_math_ocr_api_b200.evaluate import calculate_metrics, summarize, truth_string
+    ok, cer = calculate_metrics("x ^ { 2 }", "x ^ { 2 }")
+    assert ok is True and cer == 0.0
+    ok, cer = calculate_metrics("x ^ { 2 }", "x ^ { 3 }")
+    assert ok is False and abs(cer - (1 - SequenceMatcher(None, "x ^ { 2 }", "x ^ { 3 }").ratio())) < 1e-12 and 0 < cer < 0.2
+    assert calculate_metrics("", "a")[1] == 1.0
+    idx2char = {0: "<pad>", 1: "<sos>", 2: "<eos>", 3: "a", 4: "b"}
+    assert truth_string([1, 3, 4, 4, 2, 0, 0], 5, idx2char) == "a b b"
+    s = summarize([{"is_correct": True, "cer": 0.0}, {"is_correct": False, "cer": 0.5}])
+    assert s == {"accuracy": 0.5, "avg_cer": 0.25, "total_samples": 2}

@@ -447,3 +447,30 @@ def test_inference_predict_strings_match_the_reference_tokens(model, cfg, golden
     assert got == inference.ids_to_strings(tokens.cpu().tolist(), idx2char)
     ref = inference.ids_to_strings(golden_src["greedy_ys"].tolist(), idx2char)
     assert sum(a == b for a, b in zip(got, ref)) >= 3       # near-tie divergences are checked in the token test
+
+
+def test_evaluation_harness_end_to_end(model, cfg, golden_src):
+    """evaluate.evaluate_model (the runnable version of src/test_model.py): labels = the engine's own greedy output
+    give accuracy 1 / CER 0; corrupting one label lowers exactly that sample."""
+    from handwritten_math_ocr_api_b200.evaluate import evaluate_model
+    idx2char = {i: f"t{i}" for i in range(cfg.vocab_size)}
+    idx2char[model.pad_id], idx2char[model.sos_id], idx2char[model.eos_id] = "<pad>", "<sos>", "<eos>"
+    vocab = {v: k for k, v in idx2char.items()}
+    imgs = _images(golden_src).cuda()
+    tokens, steps, _ = model.generate(imgs, max_len=24)
+    caps = torch.full((4, 26), model.pad_id, dtype=torch.int64)
+    lens = []
+    for b in range(4):
+        body = [t for t in tokens[b, 1:].tolist() if t not in (model.sos_id, model.pad_id)]
+        if model.eos_id in body:
+            body = body[: body.index(model.eos_id)]
+        seq = [model.sos_id] + body + [model.eos_id]
+        caps[b, : len(seq)] = torch.tensor(seq)
+        lens.append(len(seq))
+    from handwritten_math_ocr_api_b200.config import Config
+    c = Config(); c.max_seq_len = 24
+    rows, summary = evaluate_model(model, [(imgs[:2], caps[:2], lens[:2]), (imgs[2:], caps[2:], lens[2:])], vocab, idx2char, "cuda", config=c)
+    assert summary == {"accuracy": 1.0, "avg_cer": 0.0, "total_samples": 4} and [r["image_id"] for r in rows] == [0, 1, 2, 3]
+    caps2 = caps.clone(); caps2[3, 1] = 3 if caps2[3, 1] != 3 else 4
+    rows, summary = evaluate_model(model, [(imgs, caps2, lens)], vocab, idx2char, "cuda", config=c)
+    assert summary["accuracy"] == 0.75 and rows[3]["cer"] > 0 and all(r["cer"] == 0 for r in rows[:3])
