@@ -119,6 +119,15 @@ int hmocr_generate_host(hmocr_engine* e, const float* images_host, int batch, in
                         int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
                         void* stream);
 
+/* The reference's whole image transform on the GPU, bit-identical to PIL + torchvision
+ * (/root/reference/app/src/preprocess.py:6-16: Grayscale(1) -> Resize((96,320)) -> ToTensor -> Normalize(0.5,0.5)):
+ * image_host uint8 [height, width, channels] dense, channels 1 (PIL mode "L") or 3 (mode "RGB", converted with
+ * Pillow's integer luma); PIL's antialiased bilinear resample (two passes, 22-bit fixed-point coefficients, uint8
+ * intermediate) -> image_dev f32 [1,96,320] (one slot of a [B,1,96,320] batch).  Any image size up to 16384^2.
+ * The copy of the pixels is stream-ordered; image_host may be pageable (then the call returns after staging it). */
+int hmocr_preprocess_image_u8(hmocr_engine* e, const uint8_t* image_host, int channels, int height, int width,
+                              float* image_dev, void* stream);
+
 /* Detokenise on the device (the Python loop of /root/reference/src/inference.py:29-40): for every row of
  * tokens int64 [rows, ld_tok] drop sos and pad ids wherever they occur, stop at the first eos, and write the
  * surviving ids in order to packed int32 [rows, ld_tok] (tail filled with pad) and their count to lengths int32 [rows].

@@ -474,3 +474,29 @@ def test_evaluation_harness_end_to_end(model, cfg, golden_src):
     caps2 = caps.clone(); caps2[3, 1] = 3 if caps2[3, 1] != 3 else 4
     rows, summary = evaluate_model(model, [(imgs, caps2, lens)], vocab, idx2char, "cuda", config=c)
     assert summary["accuracy"] == 0.75 and rows[3]["cer"] > 0 and all(r["cer"] == 0 for r in rows[:3])
+
+
+def test_gpu_image_preprocessing_is_bit_identical_to_pil_and_torchvision(model):
+    """hmocr_preprocess_image_u8 (grayscale + PIL antialiased bilinear resize + ToTensor + Normalize on the GPU)
+    against the reference transform itself (app/src/preprocess.py:6-16 run with the real PIL / torchvision) and the
+    numpy oracle: exact equality for up- and down-scaling, both modes, degenerate and large sizes."""
+    import numpy as np
+    from PIL import Image
+    from handwritten_math_ocr_api_b200.preprocess import preprocess_batch_gpu, preprocess_image, preprocess_image_gpu
+    from oracle.preprocess import reference_preprocess
+    rng = np.random.default_rng(11)
+    sizes = [(96, 320), (48, 160), (200, 800), (97, 321), (1, 1), (3, 1000), (500, 7), (640, 480), (95, 319),
+             (31, 333), (1200, 1600), (64, 4000)]
+    pil, want = [], []
+    for h, w in sizes:
+        for mode in ("L", "RGB"):
+            arr = rng.integers(0, 256, (h, w) if mode == "L" else (h, w, 3), dtype=np.uint8)
+            img = Image.fromarray(arr, mode=mode)
+            pil.append(img)
+            want.append(preprocess_image(img))
+            assert np.array_equal(reference_preprocess(arr), want[-1].numpy())
+    got = preprocess_batch_gpu(model, pil).cpu()
+    for i, w_ in enumerate(want):
+        assert torch.equal(got[i:i + 1], w_), (sizes[i // 2], i % 2, (got[i:i + 1] - w_).abs().max().item())
+    rgba = Image.fromarray(rng.integers(0, 256, (50, 170, 4), dtype=np.uint8), mode="RGBA")
+    assert torch.equal(preprocess_image_gpu(model, rgba).cpu(), preprocess_image(rgba.convert("RGB")))

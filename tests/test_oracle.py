@@ -179,3 +179,24 @@ def test_res18_oracle_against_reference_golden():
         # the encoder attends across the batch - an image's features depend on its batch-mates
         alone = R.encoder_forward(imgs[1:2], sd, cfg, pos)
         assert (alone - feats[1:2]).abs().max().item() > 1e-2
+
+
+def test_preprocess_oracle_matches_pil_and_torchvision():
+    """oracle/preprocess.py (restated Pillow convert + resample, torchvision ToTensor + Normalize) against the real
+    libraries run on the same pixels: the transform of app/src/preprocess.py:6-16, bit for bit, for up- and
+    down-scaling in either axis, both input modes and degenerate sizes."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from oracle.preprocess import reference_preprocess
+    t = transforms.Compose([transforms.Grayscale(num_output_channels=1), transforms.Resize((96, 320)),
+                            transforms.ToTensor(), transforms.Normalize(mean=[0.5], std=[0.5])])
+    rng = np.random.default_rng(5)
+    sizes = [(96, 320), (48, 160), (200, 800), (97, 321), (1, 1), (3, 1000), (500, 7), (640, 480), (95, 319), (31, 333)]
+    for i, (h, w) in enumerate(sizes):
+        for mode in ("L", "RGB"):
+            arr = rng.integers(0, 256, (h, w) if mode == "L" else (h, w, 3), dtype=np.uint8)
+            want = t(Image.fromarray(arr, mode=mode)).unsqueeze(0).numpy()
+            got = reference_preprocess(arr)
+            assert got.shape == want.shape == (1, 1, 96, 320)
+            assert np.array_equal(got, want), (h, w, mode, np.abs(got - want).max())
