@@ -39,6 +39,7 @@ SIGNATURES = {
     "hmocr_preprocess_u8": (_i, [_p, _p, _i, _p, _p]),
     "hmocr_pack_tokens": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "hmocr_preprocess_image_u8": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "hmocr_preprocess_cv2_u8": (_i, [_p, _p, _i, _i, _p, _p]),
     "hmocr_generate_host_u8": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hmocr_last_timings": (_i, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "hmocr_gemm_f16": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _i, _p]),

@@ -1154,6 +1154,21 @@ HM_API int hmocr_preprocess_image_u8(hmocr_engine* e, const uint8_t* image_host,
   return preprocess_image(st, src, channels, height, width, IMG_H, IMG_W, tables, mid, image_dev);
 }
 
+HM_API int hmocr_preprocess_cv2_u8(hmocr_engine* e, const uint8_t* gray_host, int height, int width, float* image_dev,
+                                   void* stream) {
+  HM_CHECK(e != nullptr && gray_host != nullptr && image_dev != nullptr, "hmocr_preprocess_cv2_u8: null argument");
+  HM_CHECK(height >= 1 && width >= 1 && height <= 16384 && width <= 16384, "hmocr_preprocess_cv2_u8: bad size %dx%d", height, width);
+  HM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* src;
+  int* tables;
+  const size_t bytes = (size_t)height * width;
+  HM_TRY(ws_get(e, "pp.src", bytes, &src));
+  HM_TRY(ws_get(e, "pp.tables", (size_t)4 * (IMG_H + IMG_W) + preprocess_table_ints(height, width, IMG_H, IMG_W), &tables));
+  HM_CUDA(cudaMemcpyAsync(src, gray_host, bytes, cudaMemcpyHostToDevice, st));
+  return preprocess_gray_cv2(st, src, height, width, IMG_H, IMG_W, tables, image_dev);
+}
+
 HM_API int hmocr_pack_tokens(hmocr_engine* e, const int64_t* tokens_dev, int rows, int ld_tok, int32_t* lengths_dev,
                              int32_t* packed_dev, void* stream) {
   HM_CHECK(e != nullptr && tokens_dev != nullptr && lengths_dev != nullptr && packed_dev != nullptr, "hmocr_pack_tokens: null argument");

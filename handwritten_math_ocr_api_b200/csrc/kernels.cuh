@@ -68,6 +68,8 @@ int permute_back(cudaStream_t st, const float* x, int B, int S, int d, float* o3
 // uint8 grayscale 96x320 images -> normalised f32 (ToTensor + Normalize(0.5, 0.5)), bit-identical to torchvision
 int preprocess_u8(cudaStream_t st, const uint8_t* in, size_t pixels, float* out);
 // full reference transform (grayscale + PIL bilinear resize + ToTensor + Normalize), preprocess_kernels.cu
+int preprocess_gray_cv2(cudaStream_t st, const uint8_t* src_dev, int H, int W, int out_h, int out_w, int* tables_dev,
+                        float* out_dev);      // the loader's cv2.resize route
 size_t preprocess_table_ints(int H, int W, int out_h, int out_w);
 int preprocess_image(cudaStream_t st, const uint8_t* src_dev, int channels, int H, int W, int out_h, int out_w,
                      int* tables_dev, uint8_t* mid_dev, float* out_dev);

@@ -8,7 +8,11 @@
 //     bits, a horizontal pass and then a vertical pass, each accumulating in int32 from 1 << 21 and clipping >> 22
 //     to uint8 (the intermediate image is uint8, as in Pillow);
 //   * ToTensor + Normalize: ((u8 / 255) - 0.5) / 0.5, every step rounded to fp32.
-// oracle/preprocess.py restates the same algorithm in numpy and is pinned against the real libraries.
+// The training / evaluation loader's route (/root/reference/src/data_loader.py:31-35) is cv2.resize(gray, (320, 96))
+// = OpenCV's 8-bit INTER_LINEAR (resize.cpp: 11-bit coefficients from a float source position, horizontal taps clamped
+// with their weight moved inwards, vertical taps clamped by row, (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2,
+// exact 2x down-scales rerouted to the 2x2 box mean) followed by the same ToTensor + Normalize: resize_cv2_kernel.
+// oracle/preprocess.py restates both algorithms in numpy and is pinned against the real libraries.
 #include <cmath>
 #include <vector>
 
@@ -56,6 +60,52 @@ __global__ void __launch_bounds__(256) resize_v_norm_kernel(const uint8_t* __res
   acc >>= PRECISION_BITS;
   const float u = (float)min(max(acc, 0), 255);
   out[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), 0.5f), 0.5f);
+}
+
+// cv2.resize INTER_LINEAR + ToTensor + Normalize, one thread per output pixel (no intermediate image):
+// tab = [x0 | x1 | xa0 | xa1] (out_w each) then [y0 | y1 | yb0 | yb1] (out_h each)
+__global__ void __launch_bounds__(256) resize_cv2_kernel(const uint8_t* __restrict__ src, int W, int area2x,
+                                                         const int* __restrict__ tab, int out_h, int out_w,
+                                                         float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_h * out_w) return;
+  const int yy = i / out_w, xx = i - yy * out_w;
+  int v;
+  if (area2x) {
+    const uint8_t* p = src + (size_t)(2 * yy) * W + 2 * xx;
+    v = (p[0] + p[1] + p[W] + p[W + 1] + 2) >> 2;
+  } else {
+    const int* ty = tab + 4 * out_w;
+    const int x0 = tab[xx], x1 = tab[out_w + xx], a0 = tab[2 * out_w + xx], a1 = tab[3 * out_w + xx];
+    const int y0 = ty[yy], y1 = ty[out_h + yy], b0 = ty[2 * out_h + yy], b1 = ty[3 * out_h + yy];
+    const uint8_t* r0 = src + (size_t)y0 * W;
+    const uint8_t* r1 = src + (size_t)y1 * W;
+    const int s0 = r0[x0] * a0 + r0[x1] * a1, s1 = r1[x0] * a0 + r1[x1] * a1;
+    v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+  }
+  const float u = (float)min(max(v, 0), 255);
+  out[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), 0.5f), 0.5f);
+}
+
+// resize.cpp: source indices and 11-bit weights of one axis (clamp_weight = the horizontal rule)
+void cv2_linear_coeffs(int ssize, int dsize, bool clamp_weight, int* i0, int* i1, int* w0, int* w1) {
+  const double inv = (double)dsize / ssize, scale = 1.0 / inv;
+  for (int d = 0; d < dsize; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(f);
+    f -= (float)s;
+    if (clamp_weight) {
+      if (s < 0) { f = 0.f; s = 0; }
+      if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+      i0[d] = s;
+      i1[d] = s + 1 < ssize ? s + 1 : ssize - 1;
+    } else {
+      i0[d] = s < 0 ? 0 : (s > ssize - 1 ? ssize - 1 : s);
+      i1[d] = s + 1 < 0 ? 0 : (s + 1 > ssize - 1 ? ssize - 1 : s + 1);
+    }
+    w0[d] = (int)std::nearbyint((1.f - f) * 2048.f);       // cvRound: round half to even
+    w1[d] = (int)std::nearbyint(f * 2048.f);
+  }
 }
 
 // Resample.c: precompute_coeffs + normalize_coeffs_8bpc, bilinear filter over the whole axis (double precision)
@@ -125,6 +175,24 @@ int preprocess_image(cudaStream_t st, const uint8_t* src_dev, int channels, int 
   resize_h_kernel<<<ceil_div(H * out_w, 256), 256, 0, st>>>(src_dev, channels, H, W * channels, d_bh, d_kh, ksh, out_w, mid_dev);
   HM_LAUNCHED();
   resize_v_norm_kernel<<<ceil_div(out_h * out_w, 256), 256, 0, st>>>(mid_dev, out_w, d_bv, d_kv, ksv, out_h, out_dev);
+  HM_LAUNCHED();
+  return 0;
+}
+
+// src_dev uint8 [H, W] dense, tables_dev >= 4 * (out_w + out_h) ints
+int preprocess_gray_cv2(cudaStream_t st, const uint8_t* src_dev, int H, int W, int out_h, int out_w, int* tables_dev,
+                        float* out_dev) {
+  HM_CHECK(H >= 1 && W >= 1 && H <= 16384 && W <= 16384, "preprocess: image size %dx%d out of range", H, W);
+  const int area2x = (W == 2 * out_w && H == 2 * out_h) ? 1 : 0;
+  if (!area2x) {
+    std::vector<int> host((size_t)4 * (out_w + out_h));
+    int* tx = host.data();
+    int* ty = host.data() + 4 * out_w;
+    cv2_linear_coeffs(W, out_w, true, tx, tx + out_w, tx + 2 * out_w, tx + 3 * out_w);
+    cv2_linear_coeffs(H, out_h, false, ty, ty + out_h, ty + 2 * out_h, ty + 3 * out_h);
+    HM_CUDA(cudaMemcpyAsync(tables_dev, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  resize_cv2_kernel<<<ceil_div(out_h * out_w, 256), 256, 0, st>>>(src_dev, W, area2x, tables_dev, out_h, out_w, out_dev);
   HM_LAUNCHED();
   return 0;
 }

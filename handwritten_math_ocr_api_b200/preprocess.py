@@ -78,3 +78,19 @@ def preprocess_batch_gpu(model, images) -> torch.Tensor:
 def preprocess_image_gpu(model, image) -> torch.Tensor:
     """``preprocess_image`` (app/src/preprocess.py:6-16) on the GPU: one image -> f32 ``[1,1,96,320]`` (device)."""
     return preprocess_batch_gpu(model, [image])
+
+
+def preprocess_dataloader_gpu(model, grays) -> torch.Tensor:
+    """The loader's route (``src/data_loader.py:31-35``: ``cv2.resize(img, (320, 96))`` + ToTensor + Normalize) on the
+    GPU for a list of grayscale uint8 arrays of any size -> f32 ``[B,1,96,320]`` (device), bit-identical to OpenCV."""
+    arrs = [_as_u8_array(g) for g in grays]
+    if any(a.ndim != 2 for a in arrs):
+        raise ValueError("the loader reads images with cv2.IMREAD_GRAYSCALE: uint8 [H,W] arrays expected")
+    out = torch.empty(len(arrs), 1, config.img_h, config.img_w, dtype=torch.float32, device=model.device)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    with torch.cuda.device(model.device):
+        for b, a in enumerate(arrs):
+            _lib.check(model._eng.lib.hmocr_preprocess_cv2_u8(model._handle(), C.c_void_p(a.ctypes.data), a.shape[0],
+                                                              a.shape[1], C.c_void_p(out[b].data_ptr()), stream),
+                       "hmocr_preprocess_cv2_u8")
+    return out

@@ -128,6 +128,12 @@ int hmocr_generate_host(hmocr_engine* e, const float* images_host, int batch, in
 int hmocr_preprocess_image_u8(hmocr_engine* e, const uint8_t* image_host, int channels, int height, int width,
                               float* image_dev, void* stream);
 
+/* The training / evaluation loader's preprocessing on the GPU, bit-identical to OpenCV + torchvision
+ * (/root/reference/src/data_loader.py:31-35: cv2.resize(gray, (320, 96)) [INTER_LINEAR] -> ToTensor -> Normalize):
+ * gray_host uint8 [height, width] (what cv2.imread(IMREAD_GRAYSCALE) returns) -> image_dev f32 [1,96,320]. */
+int hmocr_preprocess_cv2_u8(hmocr_engine* e, const uint8_t* gray_host, int height, int width, float* image_dev,
+                            void* stream);
+
 /* Detokenise on the device (the Python loop of /root/reference/src/inference.py:29-40): for every row of
  * tokens int64 [rows, ld_tok] drop sos and pad ids wherever they occur, stop at the first eos, and write the
  * surviving ids in order to packed int32 [rows, ld_tok] (tail filled with pad) and their count to lengths int32 [rows].

@@ -500,3 +500,22 @@ def test_gpu_image_preprocessing_is_bit_identical_to_pil_and_torchvision(model):
         assert torch.equal(got[i:i + 1], w_), (sizes[i // 2], i % 2, (got[i:i + 1] - w_).abs().max().item())
     rgba = Image.fromarray(rng.integers(0, 256, (50, 170, 4), dtype=np.uint8), mode="RGBA")
     assert torch.equal(preprocess_image_gpu(model, rgba).cpu(), preprocess_image(rgba.convert("RGB")))
+
+
+def test_gpu_dataloader_preprocessing_is_bit_identical_to_cv2(model):
+    """hmocr_preprocess_cv2_u8 against src/data_loader.py:31-35 run with the real OpenCV + torchvision."""
+    import cv2
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from handwritten_math_ocr_api_b200.preprocess import preprocess_dataloader_gpu
+    t = transforms.Compose([transforms.Grayscale(num_output_channels=1), transforms.Resize((96, 320)),
+                            transforms.ToTensor(), transforms.Normalize(mean=[0.5], std=[0.5])])
+    rng = np.random.default_rng(13)
+    sizes = [(96, 320), (48, 160), (192, 640), (200, 800), (97, 321), (50, 170), (500, 1300), (33, 77), (95, 319), (1, 1),
+             (2, 5), (96, 1000), (300, 320), (7, 4000), (193, 641), (24, 80), (1200, 1600)]
+    arrs = [rng.integers(0, 256, s, dtype=np.uint8) for s in sizes]
+    want = torch.stack([t(Image.fromarray(cv2.resize(a, (320, 96)), mode='L')) for a in arrs])
+    got = preprocess_dataloader_gpu(model, arrs).cpu()
+    for i in range(len(sizes)):
+        assert torch.equal(got[i], want[i]), (sizes[i], (got[i] - want[i]).abs().max().item())

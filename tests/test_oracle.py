@@ -200,3 +200,23 @@ def test_preprocess_oracle_matches_pil_and_torchvision():
             got = reference_preprocess(arr)
             assert got.shape == want.shape == (1, 1, 96, 320)
             assert np.array_equal(got, want), (h, w, mode, np.abs(got - want).max())
+
+
+def test_dataloader_preprocess_oracle_matches_cv2():
+    """oracle.preprocess.cv2_resize_linear / reference_preprocess_dataloader against the loader's own calls
+    (src/data_loader.py:31-35: cv2.resize(img, (320, 96)) -> PIL "L" -> the transform), bit for bit."""
+    import cv2
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from oracle.preprocess import cv2_resize_linear, reference_preprocess_dataloader
+    t = transforms.Compose([transforms.Grayscale(num_output_channels=1), transforms.Resize((96, 320)),
+                            transforms.ToTensor(), transforms.Normalize(mean=[0.5], std=[0.5])])
+    rng = np.random.default_rng(3)
+    for h, w in [(96, 320), (48, 160), (192, 640), (200, 800), (97, 321), (50, 170), (500, 1300), (33, 77), (95, 319),
+                 (1, 1), (2, 5), (96, 1000), (300, 320), (7, 4000), (193, 641), (24, 80)]:
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        r = cv2.resize(a, (320, 96))
+        assert np.array_equal(cv2_resize_linear(a, 96, 320), r), (h, w)
+        want = t(Image.fromarray(r, mode='L')).numpy()
+        assert np.array_equal(reference_preprocess_dataloader(a), want), (h, w)
