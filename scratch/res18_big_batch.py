@@ -9,7 +9,7 @@ from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_di
 cfg = ModelConfig()
 m = FormulaRecognitionModel(cfg.vocab_size)
 m.load_state_dict(synth_state_dict_res18(cfg, seed=0))
-pos = synth_pos_table(cfg, seed=3) if callable(synth_pos_table) else None
+pos = synth_pos_table(cfg.d_model, seed=3)
 for B in (256, 37):
     imgs = synth_images(B, seed=5).cuda()
     m.set_option("conv_impl", 1); a = m.encoder(imgs, pos).clone()
