@@ -108,6 +108,10 @@ struct hmocr_engine {
 
   struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; };
   std::map<long long, StepGraph> graphs;   // key: rows
+  // small batches: the ~95 encoder kernels are launch-bound, so generate() replays them as one captured graph
+  struct EncGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; bool warm = false; long launches = 0; };
+  std::map<int, EncGraph> enc_graphs;      // key: batch
+  int encoder_graph = 1;                   // option "encoder_graph": 0 disables (falls back by itself if capture fails)
   cudaStream_t cap_stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // enc start, enc end, dec end, poll
   cudaEvent_t poll_ev[2] = {nullptr, nullptr};
@@ -820,6 +824,53 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   return 0;
 }
 
+constexpr int ENC_GRAPH_MAX_BATCH = 32;
+
+int encode_any(hmocr_engine* e, const float* images, int B, float* enc32, h16* enc16, cudaStream_t st) {
+  return e->cfg.encoder_arch == 1 ? encode_res18_impl(e, images, B, enc32, enc16, st) : encode_impl(e, images, B, enc32, enc16, st);
+}
+
+// Encoder of a generate() call.  Up to 32 images the encoder's ~95 kernels take a few microseconds each and the
+// time is the launches: the first call at a batch size runs them eagerly (allocations, function attributes), the
+// second captures them - reading from a staging copy of the images, so the graph has no caller pointers in it -
+// and every later call is one cudaGraphLaunch.  A workspace reallocation (ws_epoch) re-captures; a capture failure
+// turns the feature off for this engine.
+int encode_for_generate(hmocr_engine* e, const float* images, int B, float* enc32, h16* enc16, cudaStream_t st) {
+  if (!e->encoder_graph || B > ENC_GRAPH_MAX_BATCH) return encode_any(e, images, B, enc32, enc16, st);
+  const size_t img_n = (size_t)B * IMG_H * IMG_W;
+  float* stage;
+  HM_TRY(ws_get(e, "gen.img_stage", img_n, &stage));
+  hmocr_engine::EncGraph& eg = e->enc_graphs[B];
+  if (!eg.warm) {                                   // first call: eager (everything gets allocated and initialised)
+    eg.warm = true;
+    return encode_any(e, images, B, enc32, enc16, st);
+  }
+  if (eg.exec == nullptr || eg.epoch != e->ws_epoch) {
+    if (eg.exec != nullptr) { cudaGraphExecDestroy(eg.exec); eg.exec = nullptr; }
+    const uint64_t epoch_before = e->ws_epoch;
+    cudaGraph_t graph = nullptr;
+    HM_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const long launches_before = g_launch_count;
+    const int rc = encode_any(e, stage, B, enc32, enc16, e->cap_stream);
+    eg.launches = g_launch_count - launches_before;
+    g_launch_count = launches_before;               // captured, not launched
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc == 0 && ce == cudaSuccess && e->ws_epoch == epoch_before) ce = cudaGraphInstantiate(&eg.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != 0 || ce != cudaSuccess || e->ws_epoch != epoch_before || eg.exec == nullptr) {
+      (void)cudaGetLastError();
+      eg.exec = nullptr;
+      e->encoder_graph = 0;                         // never again on this engine; the eager path is always correct
+      return encode_any(e, images, B, enc32, enc16, st);
+    }
+    eg.epoch = e->ws_epoch;
+  }
+  HM_CUDA(cudaMemcpyAsync(stage, images, img_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  HM_CUDA(cudaGraphLaunch(eg.exec, st));
+  g_launch_count += eg.launches;
+  return 0;
+}
+
 int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int beam, int64_t* tokens, float* logprob,
                   int32_t* steps, float* score, cudaStream_t st) {
   float* enc32;
@@ -827,8 +878,7 @@ int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int 
   HM_TRY(ws_get(e, "gen.enc32", (size_t)B * e->mem_len * e->cfg.d_model, &enc32));
   HM_TRY(ws_get(e, "gen.enc16", (size_t)B * e->mem_len * e->cfg.d_model, &enc16));
   HM_CUDA(cudaEventRecord(e->ev[0], st));
-  if (e->cfg.encoder_arch == 1) HM_TRY(encode_res18_impl(e, images, B, enc32, enc16, st));
-  else HM_TRY(encode_impl(e, images, B, enc32, enc16, st));
+  HM_TRY(encode_for_generate(e, images, B, enc32, enc16, st));
   HM_CUDA(cudaEventRecord(e->ev[1], st));
   HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));
   HM_CUDA(cudaEventRecord(e->ev[2], st));
@@ -887,6 +937,8 @@ HM_API void hmocr_destroy(hmocr_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : e->enc_graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto& kv : e->ws)
     if (kv.second.p) cudaFree(kv.second.p);
@@ -1047,6 +1099,9 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     e->steps_per_launch = value;
   } else if (n == "trace_step") {
     e->trace_step = value;
+  } else if (n == "encoder_graph") {
+    HM_CHECK(value == 0 || value == 1, "encoder_graph must be 0 or 1");
+    e->encoder_graph = value;
   } else if (n == "conv_impl") {
     HM_CHECK(value == 0 || value == 1, "conv_impl must be 0 (implicit GEMM) or 1 (im2col)");
     e->conv_impl = value;

@@ -519,3 +519,22 @@ def test_gpu_dataloader_preprocessing_is_bit_identical_to_cv2(model):
     got = preprocess_dataloader_gpu(model, arrs).cpu()
     for i in range(len(sizes)):
         assert torch.equal(got[i], want[i]), (sizes[i], (got[i] - want[i]).abs().max().item())
+
+
+@pytest.mark.parametrize("batch", [1, 3, 8, 32])
+def test_small_batch_encoder_graph_replays_the_same_bits(sd, cfg, golden_src, batch):
+    """generate() on <= 32 images: call 1 runs the encoder eagerly, call 2 captures it into a CUDA graph, calls 3+
+    replay it from a staging copy of the images.  Tokens and log-probs must be the bits of the kernel-by-kernel
+    path (encoder_graph = 0), for changing image contents too."""
+    from handwritten_math_ocr_api_b200 import FormulaRecognitionModel
+    from handwritten_math_ocr_api_b200.synthetic import synth_images
+    m = FormulaRecognitionModel(cfg.vocab_size)
+    m.load_state_dict(sd)
+    sets = [synth_images(batch, seed=500 + i).cuda() for i in range(4)]
+    m.set_option("encoder_graph", 0)
+    want = [m.generate(x, max_len=24, return_logprobs=True) for x in sets]
+    m.set_option("encoder_graph", 1)
+    for rep in range(2):
+        for x, w in zip(sets, want):
+            tok, steps, lp = m.generate(x, max_len=24, return_logprobs=True)
+            assert steps == w[1] and torch.equal(tok, w[0]) and torch.equal(lp, w[2])
