@@ -431,10 +431,11 @@ template <int NB, int KB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   constexpr bool BEAM = KB > 0;
-  // K/V register pipeline depth (blocks of 32 keys in flight per warp).  Two slots beat four for greedy decoding
-  // (B=256: 17.65 -> 16.7 ms; B=64: 88.9 -> 84.4 us/step): 32 fewer live registers and smaller L2 bursts outweigh the
-  // extra round trip on long histories.  The beam kernel keeps four.
-  constexpr int KVS = BEAM ? 4 : 2;
+  // K/V register pipeline depth (blocks of 32 keys in flight per warp).  For greedy decoding ONE slot beats two, three
+  // and four (B=256 decode: 16.6 / 16.7 / 17.1 / 17.65 ms; B=64: 83.7 / 84.2 / 85.6 / 88.9 us per step): the 16 warps of
+  // an SM and the L2 prefetch a layer ahead already cover the latency, and every slot costs 16 live registers at the
+  // 128-register cap (one slot: no spills at all).  The beam kernel keeps four.
+  constexpr int KVS = BEAM ? 4 : 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
