@@ -623,11 +623,9 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       const __half* Vc = p.vcache + set_rd + (size_t)l * kv_layer + kv_src;
       __half* Kd = p.kcache + set_wr + (size_t)l * kv_layer + kv_row;           // where this step's key / value go
       __half* Vd = p.vcache + set_wr + (size_t)l * kv_layer + kv_row;
-      const __half* Mk = p.memk + (size_t)l * m_layer + m_row;
-      const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
       TR();
       // ---- self-attention: q, k, v of head c = 6 tiles ---------------------------------------------
-      if (lane < 2 && !(p.flags & 2)) prefetch_l2(lane ? Mv : Mk, 2048);   // this layer's memory K/V -> L2
+      if (lane < 2 && !(p.flags & 2)) prefetch_l2((lane ? p.memv : p.memk) + (size_t)l * m_layer + m_row, 2048);   // this layer's memory K/V -> L2
       {
         const int j = (warp - g) & 7;
         if (j < 6) {
@@ -679,7 +677,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       TR();
       // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
-      LnRegs ln = load_ln(l, 0);
       xwait(X_CTX, ph_ctx, XB_CTX);
       TR();
       {
@@ -697,6 +694,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         g += 2;
       }
       TR();
+      LnRegs ln = load_ln(l, 0);          // fetched while y is in flight: not live across the GEMM above
       xwait(X_Y, ph_y, XB_Y);
       TR();
       layer_norm(ln);
@@ -717,6 +715,8 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         }
         g += 2;
       }
+      const __half* Mk = p.memk + (size_t)l * m_layer + m_row;       // (not live across the self-attention block)
+      const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
       attend_issue<1, KVS>(Mk, p.mem_len, lane, kv);
       __syncthreads();
       TR();
@@ -726,7 +726,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         send_ctx(o);
       }
       TR();
-      ln = load_ln(l, 1);
       xwait(X_CTX, ph_ctx, XB_CTX);
       TR();
       {
@@ -744,6 +743,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         g += 2;
       }
       TR();
+      ln = load_ln(l, 1);
       xwait(X_Y, ph_y, XB_Y);
       TR();
       layer_norm(ln);
@@ -771,7 +771,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         g += 4;
       }
       TR();
-      ln = load_ln(l, 2);
       xwait(X_HF, ph_hf, XB_HF);
       TR();
       {
@@ -789,6 +788,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         g += 4;
       }
       TR();
+      ln = load_ln(l, 2);
       xwait(X_Y, ph_y, XB_Y);
       TR();
       layer_norm(ln);
