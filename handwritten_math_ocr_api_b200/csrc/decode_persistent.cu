@@ -427,10 +427,13 @@ __device__ __forceinline__ float chunk_bias(const uint8_t* slot, int r) {
 }
 
 // KB = 0: greedy.  KB = DP_MAX_BEAM: beam search with p.beam <= KB hypotheses per image (see decode_persistent.cuh).
-template <int NB, int KB>
+// DEV = true: the instrumented build (phase tracing, the timing-experiment flags); the production instantiations
+// carry none of that code.
+template <int NB, int KB, bool DEV>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   constexpr bool BEAM = KB > 0;
+  const int dev_flags = DEV ? p.flags : 0;
   // K/V register pipeline depth (blocks of 32 keys in flight per warp).  For greedy decoding ONE slot beats two, three
   // and four (B=256 decode: 16.6 / 16.7 / 17.1 / 17.65 ms; B=64: 83.7 / 84.2 / 85.6 / 88.9 us per step): the 16 warps of
   // an SM and the L2 prefetch a layer ahead already cover the latency, and every slot costs 16 live registers at the
@@ -470,7 +473,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       bulk_g2s(s.slot[warp], wst + (size_t)wpos * DP_CHUNK, DP_CHUNK, &s.full[warp]);
     }
   };
-  const bool dbg_noweights = (p.flags & 4) != 0;      // timing experiments only (results are wrong)
+  const bool dbg_noweights = (dev_flags & 4) != 0;      // timing experiments only (results are wrong)
   auto slot_wait = [&]() { if (!dbg_noweights || wk == 0) mbar_wait(&s.full[warp], wk & 1); };
   auto slot_release = [&]() {
     __syncwarp();
@@ -606,7 +609,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   const int my_img = my_row / p.beam;
   const size_t m_layer = (size_t)p.images * NH * 1024, m_row = ((size_t)my_img * NH + c) * 1024;
   int g = 0;     // stream index of the next chunk (chunk g + j belongs to warp (g + j) % 8)
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool tracing = DEV && p.trace != nullptr && blockIdx.x == 0 && tid == 0;
   int ti = 0;
 #define TR() do { if (tracing && t == p.trace_step && ti < 1024) p.trace[ti++] = clock64(); } while (0)
   for (int t = t_begin; t < t_end; ++t) {
@@ -625,7 +628,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       __half* Vd = p.vcache + set_wr + (size_t)l * kv_layer + kv_row;
       TR();
       // ---- self-attention: q, k, v of head c = 6 tiles ---------------------------------------------
-      if (lane < 2 && !(p.flags & 2)) prefetch_l2((lane ? p.memv : p.memk) + (size_t)l * m_layer + m_row, 2048);   // this layer's memory K/V -> L2
+      if (lane < 2 && !(dev_flags & 2)) prefetch_l2((lane ? p.memv : p.memk) + (size_t)l * m_layer + m_row, 2048);   // this layer's memory K/V -> L2
       {
         const int j = (warp - g) & 7;
         if (j < 6) {
@@ -649,7 +652,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         g += 6;
       }
       KvSlots<KVS> kv;
-      const int nhist = (p.flags & 8) ? min(t, 1) : t;
+      const int nhist = (dev_flags & 8) ? min(t, 1) : t;
       attend_issue<NB, KVS>(Kc, nhist, lane, kv);       // history K blocks fly across the barrier
       TR();
       __syncthreads();
@@ -670,7 +673,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         // self-attention cache of the NEXT layer (next step's layer 0 after the last one) -> L2
         const bool last = l + 1 == L;
         const int keys = last ? t + 1 : t;
-        if (keys > 0 && lane < 2 && !(p.flags & 1)) {
+        if (keys > 0 && lane < 2 && !(dev_flags & 1)) {
           const size_t nxt = last ? set_wr + kv_row : set_rd + (size_t)(l + 1) * kv_layer + kv_src;
           prefetch_l2((lane ? p.vcache : p.kcache) + nxt, ((keys + 31) >> 5) * 2048);
         }
@@ -1060,10 +1063,11 @@ int g_max_clusters = 0;
 int decode_persistent_init() {
   static bool done = false;
   if (done) return 0;
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, DP_MAX_BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, DP_MAX_BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, DP_MAX_BEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, DP_MAX_BEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL * 64);
   cfg.blockDim = dim3(THREADS);
@@ -1072,7 +1076,7 @@ int decode_persistent_init() {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<5, 0>, &cfg));
+  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<5, 0, false>, &cfg));
   HM_CHECK(g_max_clusters >= 1, "device cannot host an 8-CTA decode cluster");
   done = true;
   return 0;
@@ -1104,12 +1108,16 @@ int decode_persistent_launch(cudaStream_t st, DecPersistParams p, int t_begin, i
   }
   p.num_clusters = ceil_div(p.rows, p.rows_per_cluster);
   dim3 grid(p.num_clusters * CL);
-  if (p.tmax <= 160) {
-    if (beam) decode_persistent_kernel<5, DP_MAX_BEAM><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
-    else decode_persistent_kernel<5, 0><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+  const bool dev = p.trace != nullptr || p.flags != 0;       // instrumented build: greedy, <= 160 positions only
+  if (dev) {
+    HM_CHECK(!beam && p.tmax <= 160, "decode: tracing / experiment flags need greedy decoding and max_seq_len <= 160");
+    decode_persistent_kernel<5, 0, true><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+  } else if (p.tmax <= 160) {
+    if (beam) decode_persistent_kernel<5, DP_MAX_BEAM, false><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    else decode_persistent_kernel<5, 0, false><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
   } else {
-    if (beam) decode_persistent_kernel<8, DP_MAX_BEAM><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
-    else decode_persistent_kernel<8, 0><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    if (beam) decode_persistent_kernel<8, DP_MAX_BEAM, false><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
+    else decode_persistent_kernel<8, 0, false><<<grid, THREADS, sizeof(Smem), st>>>(p, t_begin, t_end);
   }
   HM_LAUNCHED();
   return 0;
