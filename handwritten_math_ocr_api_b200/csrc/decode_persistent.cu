@@ -131,9 +131,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     if (ok) return;
     if (t0 == 0) t0 = clock64();
     else if (clock64() - t0 > 4000000000LL) {
-      printf("hmocr: exchange mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+      __trap();                     // a protocol bug fails the launch instead of hanging the GPU (no printf: code size)
     }
+  }
+}
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {       // common.cuh mbar_wait without the printf
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -474,7 +480,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     }
   };
   const bool dbg_noweights = (dev_flags & 4) != 0;      // timing experiments only (results are wrong)
-  auto slot_wait = [&]() { if (!dbg_noweights || wk == 0) mbar_wait(&s.full[warp], wk & 1); };
+  auto slot_wait = [&]() { if (!dbg_noweights || wk == 0) mbar_wait_trap(&s.full[warp], wk & 1); };
   auto slot_release = [&]() {
     __syncwarp();
     ++wk; wgi += NW; wpos += NW;
