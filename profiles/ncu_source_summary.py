@@ -16,25 +16,29 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    cur, files, H = None, {}, None
+    cur, files, H, hdr = None, {}, None, {}
     for r in rows:
         if r and r[0] == "File Path":
             cur = r[1]; files[cur] = []; continue
         if r and r[0] == "Line No":
-            H = r; continue
+            H = r
+            hdr[cur] = r
+            continue
         if r and r[0] == "Function Name":
             continue
         if cur and len(r) > 8:
             files[cur].append(r)
-    st = [i for i, h in enumerate(H) if h.startswith("stall_") and "Not Issued" not in h]
     tot = {}
     allsamp = allinst = 0
     for f, rs in files.items():
+        Hf = hdr.get(f, H)                                   # every file section has its own header row
+        stf = [i for i, h in enumerate(Hf) if h.startswith("stall_") and "Not Issued" not in h]
         for r in rs:
-            if r[0].strip().isdigit():
+            if r[0].strip().isdigit() and len(r) == len(Hf):
                 allsamp += I(r[4]); allinst += I(r[7])
-                for i in st:
-                    tot[H[i][6:]] = tot.get(H[i][6:], 0) + I(r[i])
+                for i in stf:
+                    tot[Hf[i][6:]] = tot.get(Hf[i][6:], 0) + I(r[i])
+    st = [i for i, h in enumerate(H) if h.startswith("stall_") and "Not Issued" not in h]
     print(f"samples {allsamp}  warp instructions {allinst}")
     print("stall reasons:", {k: v for k, v in sorted(tot.items(), key=lambda kv: -kv[1]) if v})
     for f, rs in files.items():
