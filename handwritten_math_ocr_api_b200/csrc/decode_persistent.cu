@@ -488,10 +488,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     if (lane == 0 && !dbg_noweights) slot_fetch();
   };
   // ---- exchanges --------------------------------------------------------------------------------------
-  uint32_t ph_ctx = 0, ph_y = 0, ph_hf = 0, ph_part = 0, ph_top = 0;
-  auto xwait = [&](int X, uint32_t& ph, uint32_t bytes) {
-    mbar_wait_cluster(&s.xbar[X], ph & 1);
-    ++ph;
+  // The mbarrier phase parities follow from two counters instead of one per exchange: per layer the context barrier
+  // completes twice (parities 0, 1), the y barrier three times (parity (layer + site) & 1), the hidden barrier once
+  // (layer & 1); partials / top-K lists once per step.
+  uint32_t nlayer = 0, nstep = 0;            // layers / steps done since the launch started
+  auto xwait = [&](int X, uint32_t parity, uint32_t bytes) {
+    mbar_wait_cluster(&s.xbar[X], parity & 1);
     if (tid == 0) mbar_expect_tx(&s.xbar[X], bytes);      // arm the next phase
   };
   auto send_all = [&](const void* local_dst, uint4 v, int X) {    // the same 16 bytes to all 8 CTAs
@@ -686,7 +688,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       TR();
       // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
-      xwait(X_CTX, ph_ctx, XB_CTX);
+      xwait(X_CTX, 0u, XB_CTX);
       TR();
       {
         const int j = (warp - g) & 7;
@@ -704,7 +706,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       TR();
       LnRegs ln = load_ln(l, 0);          // fetched while y is in flight: not live across the GEMM above
-      xwait(X_Y, ph_y, XB_Y);
+      xwait(X_Y, nlayer, XB_Y);
       TR();
       layer_norm(ln);
       __syncthreads();
@@ -735,7 +737,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         send_ctx(o);
       }
       TR();
-      xwait(X_CTX, ph_ctx, XB_CTX);
+      xwait(X_CTX, 1u, XB_CTX);
       TR();
       {
         const int j = (warp - g) & 7;
@@ -753,7 +755,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       TR();
       ln = load_ln(l, 1);
-      xwait(X_Y, ph_y, XB_Y);
+      xwait(X_Y, nlayer + 1u, XB_Y);
       TR();
       layer_norm(ln);
       __syncthreads();
@@ -780,7 +782,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         g += 4;
       }
       TR();
-      xwait(X_HF, ph_hf, XB_HF);
+      xwait(X_HF, nlayer, XB_HF);
       TR();
       {
         const int j = (warp - g) & 7;
@@ -798,7 +800,8 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       TR();
       ln = load_ln(l, 2);
-      xwait(X_Y, ph_y, XB_Y);
+      xwait(X_Y, nlayer, XB_Y);   // third of the layer: (layer + 2) & 1
+      ++nlayer;
       TR();
       layer_norm(ln);
       __syncthreads();
@@ -878,7 +881,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         st_async_v4(off + 32, v2, bar);
       }
     }
-    xwait(X_PART, ph_part, XB_PART);
+    xwait(X_PART, nstep, XB_PART);
     TR();
     Partial a;                               // row `warp`: (max, argmax, sum-exp) over the whole vocabulary
     if (lane < CL) a = s.part[lane][warp];
@@ -903,7 +906,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
     } else {
       // ---- beam step (oracle/decode.py::beam_search): candidates -> K best per image -> new hypotheses -----
-      xwait(X_TOP, ph_top, XB_TOP);
+      xwait(X_TOP, nstep, XB_TOP);
       TopK<KB> tl;
       if (lane < CL) tl.load(s.ctop[lane][warp]); else tl.init();
 #pragma unroll
@@ -965,6 +968,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
     }
     // ---- next input: embedding[token] + pos[t+1] ---------------------------------------------------
+    ++nstep;
     if (t + 1 < p.max_pos) embed_row(t + 1, tok);
     __syncthreads();
     if (BEAM && tid == 0 && c == 0 && !cluster_done) {
