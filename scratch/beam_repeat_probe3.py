@@ -8,11 +8,17 @@ cfg = ModelConfig()
 m = FormulaRecognitionModel(cfg.vocab_size)
 m.load_state_dict(synth_state_dict(cfg, seed=0))
 N = int(sys.argv[1]); NIMG = int(sys.argv[2]); BEAM = int(sys.argv[3]); SPL = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-if BEAM == 1:
+GREEDY = BEAM == 0
+if GREEDY:
+    BEAM = 1
+elif BEAM == 1:
     m.set_option("force_beam_kernel", 1)
 if SPL:
     m.set_option("steps_per_launch", SPL)
-imgs = synth_images(8, seed=99).cuda().repeat(9, 1, 1, 1)[:NIMG].contiguous()
+FLAGS = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+if FLAGS:
+    m.set_option("dbg_flags", FLAGS)
+imgs = synth_images(8, seed=99).cuda().repeat((NIMG + 7) // 8, 1, 1, 1)[:NIMG].contiguous()
 feats = m.encoder(imgs)
 per_image = [collections.Counter() for _ in range(NIMG)]
 for rep in range(N):
@@ -21,4 +27,4 @@ for rep in range(N):
     for i, v in enumerate(sc.tolist()):
         per_image[i][v] += 1
 multi = [(i, dict(c)) for i, c in enumerate(per_image) if len(c) > 1]
-print(f"beam {BEAM} images {NIMG} spl {SPL}: images with more than one score value: {len(multi)} of {NIMG}; deviating runs: {sum(sum(c.values()) - max(c.values()) for _, c in [(i, per_image[i]) for i in range(NIMG)])}")
+print(f"{'greedy kernel ' if GREEDY else ''}beam {BEAM} images {NIMG} spl {SPL} flags {FLAGS}: images with more than one score value: {len(multi)} of {NIMG}; deviating runs: {sum(sum(c.values()) - max(c.values()) for _, c in [(i, per_image[i]) for i in range(NIMG)])}")
