@@ -483,6 +483,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   auto slot_wait = [&]() { if (!dbg_noweights || wk == 0) mbar_wait_trap(&s.full[warp], wk & 1); };
   auto slot_release = [&]() {
     __syncwarp();
+    // The warp has read the slot through the generic proxy (ldmatrix, the bias words); the refill below writes it
+    // through the async proxy (TMA).  Without this cross-proxy fence the two are not ordered: under heavy memory
+    // traffic (two CTAs per SM) about 1 % of the (image, run) pairs of a B = 256 decode came back with slightly
+    // different log-probabilities - a few elements of the NEXT weight tile leaking into the current one
+    // (found with scratch/beam_repeat_probe3.py and scratch/poison_probe.py).
+    fence_proxy_async();
     ++wk; wgi += NW; wpos += NW;
     if (wpos >= S) wpos -= S;
     if (lane == 0 && !dbg_noweights) slot_fetch();
@@ -678,15 +684,14 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
           if (lane < 16) reinterpret_cast<uint32_t*>(Kd)[k_app] = reinterpret_cast<const uint32_t*>(&s.knew[warp][0])[lane];
           Vd[v_app] = s.vnew[warp][lane];
         }
-        // No prefetch of the next layer's self-attention cache.  One used to be issued here
-        // (cp.async.bulk.prefetch.L2, a layer ahead; worth 1.1 ms of a B=256 decode), but with it the results were
-        // timing dependent: at two CTAs per SM ~1 % of the (image, run) pairs of a greedy decode and 0.3 % of a
-        // beam-5 decode came back with slightly different log-probabilities (tokens unchanged).  A generic-proxy
-        // prefetch.global.L2 made it 14 %, plain ld.global.cg "touch" loads 1.8 %, gpu-scope loads and fences
-        // changed nothing, and without any early access 0 of 85,000 pairs deviate
-        // (scratch/beam_repeat_probe3.py).  Since ordinary loads cannot corrupt memory, an early access to these
-        // lines exposes an ordering problem between the append stores and later reads that is not understood yet
-        // (DESIGN.md 4.4); until it is, nothing touches a cache line ahead of the attention that needs it.
+        // self-attention cache of the NEXT layer (next step's layer 0 after the last one) -> L2.  Greedy only: in
+        // beam search the parent row is not known a step ahead (the beam kernel is 2 % faster without it).
+        const bool last = l + 1 == L;
+        const int keys = last ? t + 1 : t;
+        if (!BEAM && keys > 0 && lane < 2 && !(dev_flags & 1)) {
+          const size_t nxt = last ? set_wr + kv_row : set_rd + (size_t)(l + 1) * kv_layer + kv_src;
+          prefetch_l2((lane ? p.vcache : p.kcache) + nxt, ((keys + 31) >> 5) * 2048);
+        }
       }
       TR();
       // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
