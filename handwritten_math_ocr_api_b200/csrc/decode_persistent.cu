@@ -440,11 +440,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   constexpr bool BEAM = KB > 0;
   const int dev_flags = DEV ? p.flags : 0;
-  // K/V register pipeline depth (blocks of 32 keys in flight per warp).  For greedy decoding ONE slot beats two, three
-  // and four (B=256 decode: 16.6 / 16.7 / 17.1 / 17.65 ms; B=64: 83.7 / 84.2 / 85.6 / 88.9 us per step): the 16 warps of
-  // an SM and the L2 prefetch a layer ahead already cover the latency, and every slot costs 16 live registers at the
-  // 128-register cap (one slot: no spills at all).  The beam kernel keeps four.
-  constexpr int KVS = BEAM ? 4 : 1;
+  // K/V register pipeline depth (blocks of 32 keys in flight per warp).  ONE slot beats two, three and four (greedy B=256
+  // decode: 16.6 / 16.7 / 17.1 / 17.65 ms; beam 5 at 64 images: 266 vs 290 us per step with four): the 16 warps of an SM
+  // already cover the latency - the attention phases are bound by the L2 -> SM ingest of the K/V bytes - and every slot
+  // costs 16 live registers at the 128-register cap (one slot: no spills in the greedy kernel, 4 bytes in the beam kernel).
+  constexpr int KVS = 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
