@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(HERE, "libhmocr.so")
 
 class HmocrConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("vocab_size", "d_model", "nhead", "dim_feedforward", "num_layers",
-                                         "max_seq_len", "sos_id", "eos_id", "pad_id", "encoder_arch")]
+                                         "max_seq_len", "sos_id", "eos_id", "pad_id", "encoder_arch",
+                                         "enc_num_layers")]
 
 
 _p, _i, _i64p, _fp = C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p
@@ -29,7 +30,9 @@ SIGNATURES = {
     "hmocr_finalize_weights": (_i, [_p]),
     "hmocr_set_option": (_i, [_p, C.c_char_p, _i]),
     "hmocr_decode_max_clusters": (_i, [C.POINTER(C.c_int)]),
-    "hmocr_set_pos_table": (_i, [_p, _p, _i, _i]),
+    "hmocr_set_pos_table": (_i, [_p, _p, _i, _i, _p]),
+    "hmocr_workspace_bytes": (_i, [_p, _i, _i, _i, C.POINTER(C.c_size_t)]),
+    "hmocr_set_workspace": (_i, [_p, _p, C.c_size_t, _p]),
     "hmocr_read_trace": (_i, [_p, _i64p, _i]),
     "hmocr_encode": (_i, [_p, _p, _i, _p, _p]),
     "hmocr_decoder_forward": (_i, [_p, _p, _p, _i, _i, _p, _p]),

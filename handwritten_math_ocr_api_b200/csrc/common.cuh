@@ -53,6 +53,22 @@ extern thread_local long g_launch_count;      // kernels launched by this librar
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Function attributes (the > 48 KB dynamic shared memory opt-in), SM counts and occupancy numbers belong to a DEVICE,
+// not to the process: FormulaRecognitionModel(device='cuda:1') next to one on cuda:0 must run its own set-up.
+// HM_DEVICE_ONCE(body) runs `body` the first time the calling site is reached with each device current (`_dev`).
+#define HM_MAX_DEVICES 64
+#define HM_DEVICE_ONCE(...)                                                    \
+  do {                                                                         \
+    static unsigned long long _done_mask = 0;                                  \
+    int _dev = 0;                                                              \
+    HM_CUDA(cudaGetDevice(&_dev));                                             \
+    HM_CHECK(_dev >= 0 && _dev < HM_MAX_DEVICES, "device index %d", _dev);     \
+    if (!((__atomic_load_n(&_done_mask, __ATOMIC_ACQUIRE) >> _dev) & 1ull)) {  \
+      __VA_ARGS__;                                                             \
+      __atomic_fetch_or(&_done_mask, 1ull << _dev, __ATOMIC_RELEASE);          \
+    }                                                                          \
+  } while (0)
+
 // Programmatic dependent launch: the encoder is ~95 short kernels on one stream, and a plain launch only starts
 // once the previous grid has drained.  Kernels launched through launch_pdl() may start (block scheduling, shared
 // memory carve-out, barrier / TMEM set-up, loads of weights) while the previous kernel's last CTAs still run;

@@ -907,8 +907,13 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         if (p.logprob != nullptr) p.logprob[(size_t)gr * p.max_len + t] = -logf(a.s);   // log_softmax of the argmax
         if (tok == p.eos && !p.finished[gr]) {
           p.finished[gr] = 1;
+          // src/inference.py:23-25 stops after the step at which the LAST row emits its first eos = the maximum of
+          // (first-eos step + 1) over the rows.  Clusters are not in lockstep (and run in waves), so the thread that
+          // completes the count publishes that maximum, not its own t.
+          atomicMax(&p.state->last_eos, t + 1);
+          __threadfence();
           const int cnt = atomicAdd(&p.state->finished_count, 1) + 1;
-          if (cnt == p.rows) p.state->steps_executed = t + 1;      // src/inference.py:23-25
+          if (cnt == p.rows) p.state->steps_executed = atomicMax(&p.state->last_eos, 0);
         }
       }
     } else {
@@ -983,8 +988,10 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       for (int r = 0; r < nrows; ++r) all = all && s.bfin[r] != 0;
       if (all) {
         cluster_done = true;
+        atomicMax(&p.state->last_eos, t + 1);          // see the greedy branch: the last cluster in TIME publishes the max
+        __threadfence();
         const int cnt = atomicAdd(&p.state->finished_count, 1) + 1;
-        if (cnt == p.num_clusters) p.state->steps_executed = t + 1;
+        if (cnt == p.num_clusters) p.state->steps_executed = atomicMax(&p.state->last_eos, 0);
       }
     }
     TR();
@@ -1041,7 +1048,7 @@ __global__ void __launch_bounds__(256) repack_memkv_kernel(const float* __restri
 __global__ void beam_init_kernel(DecodeState* state, float* bm_score, int* bm_fin, int* bm_src, int* bm_tok, int rows,
                                  int beam, int rows_per_cluster, int sos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { state->step = 0; state->finished_count = 0; state->steps_executed = 0; state->pad_ = 0; }
+  if (i == 0) { state->step = 0; state->finished_count = 0; state->steps_executed = 0; state->last_eos = 0; }
   if (i < rows) {
     bm_score[i] = (i % beam == 0) ? 0.f : -INFINITY;     // all hypotheses start as [sos]: only the first one counts
     bm_fin[i] = 0;
@@ -1073,35 +1080,39 @@ __global__ void beam_finalize_kernel(const DecodeState* state, const float* bm_s
   }
 }
 
-int g_max_clusters = 0;
+int g_max_clusters[HM_MAX_DEVICES] = {};      // co-resident 8-CTA clusters, per device
 
 }  // namespace
 
+// Per DEVICE (function attributes and the occupancy answer belong to a device, not to the process).
 int decode_persistent_init() {
-  static bool done = false;
-  if (done) return 0;
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, DP_MAX_BEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, DP_MAX_BEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL * 64);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = sizeof(Smem);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  HM_CUDA(cudaOccupancyMaxActiveClusters(&g_max_clusters, decode_persistent_kernel<5, 0, false>, &cfg));
-  HM_CHECK(g_max_clusters >= 1, "device cannot host an 8-CTA decode cluster");
-  done = true;
+  HM_DEVICE_ONCE({
+    HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<5, DP_MAX_BEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    HM_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<8, DP_MAX_BEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 64);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = sizeof(Smem);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    HM_CUDA(cudaOccupancyMaxActiveClusters(&n, decode_persistent_kernel<5, 0, false>, &cfg));
+    HM_CHECK(n >= 1, "device cannot host an 8-CTA decode cluster");
+    g_max_clusters[_dev] = n;
+  });
   return 0;
 }
 
 int decode_persistent_max_clusters(int* out) {
   HM_TRY(decode_persistent_init());
-  *out = g_max_clusters;
+  int dev = 0;
+  HM_CUDA(cudaGetDevice(&dev));
+  *out = g_max_clusters[dev];
   return 0;
 }
 

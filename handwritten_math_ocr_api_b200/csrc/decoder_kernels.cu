@@ -224,7 +224,7 @@ __global__ void advance_step_kernel(DecodeState* state) { state->step += 1; }
 __global__ void init_decode_kernel(DecodeState* state, int64_t* tokens, int ld_tok, int rows, int sos, int pad,
                                    uint8_t* finished, float* logprob, int max_len) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { state->step = 0; state->finished_count = 0; state->steps_executed = 0; state->pad_ = 0; }
+  if (i == 0) { state->step = 0; state->finished_count = 0; state->steps_executed = 0; state->last_eos = 0; }
   if (i < rows) finished[i] = 0;
   const int total = rows * ld_tok;
   for (int k = i; k < total; k += gridDim.x * blockDim.x) tokens[k] = (k % ld_tok == 0) ? sos : pad;

@@ -12,6 +12,8 @@
 #include "hmocr.h"
 #include "kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a profiler injects the NVTX library
+
 #define HM_API extern "C" __attribute__((visibility("default")))
 
 namespace hmocr {
@@ -27,6 +29,10 @@ void set_error(const char* fmt, ...) {
 }
 
 namespace {
+
+// NVTX ranges around the phases of a generate call: encode / cross-KV / decode launch k
+inline void nvtx_push(const char* name) { nvtxRangePushA(name); }
+inline void nvtx_pop() { nvtxRangePop(); }
 
 constexpr int IMG_H = 96, IMG_W = 320, SWIN_OUT = 768;
 constexpr int RES18_MEM = 10, SWIN_MEM = 30;
@@ -102,9 +108,20 @@ struct hmocr_engine {
   int conv_impl = 0;                  // ResNet trunk: 0 = implicit GEMM (TMA patches), 1 = explicit im2col + GEMM
   int force_beam_kernel = 0;          // run beam = 1 through the beam-search kernel (A/B test against greedy)
 
-  // scratch (grow-only); any reallocation invalidates the captured step graphs
+  // Scratch buffers, addressed by name; any (re)placement invalidates the captured graphs (ws_epoch).
+  //  * caller-owned (SURVEY.md 8b "Ownership"): hmocr_set_workspace hands the engine ONE buffer (a torch tensor on the
+  //    Python side, sized by hmocr_workspace_bytes); names are bump-allocated inside it and the engine allocates nothing.
+  //  * engine-owned (no hmocr_set_workspace call): stream-ordered cudaMallocAsync / cudaFreeAsync on the caller's
+  //    stream - no cudaDeviceSynchronize, no device-wide stall on growth.
   std::map<std::string, Buf> ws;
   uint64_t ws_epoch = 0;
+  uint8_t* ext_ws = nullptr;          // caller-owned pool
+  size_t ext_cap = 0, ext_used = 0;
+  cudaStream_t cur_stream = nullptr;  // stream of the API call in progress (engine-owned allocations are ordered on it)
+  bool planning = false;              // hmocr_workspace_bytes: the schedules only record their buffer sizes
+  std::map<std::string, size_t> plan;
+  std::map<std::string, size_t> planned;   // per-buffer maximum over every hmocr_workspace_bytes call: placements use it,
+                                           // so a small call followed by a large one never places a buffer twice
 
   struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; };
   std::map<long long, StepGraph> graphs;   // key: rows
@@ -123,20 +140,44 @@ struct hmocr_engine {
 namespace hmocr {
 namespace {
 
+constexpr size_t WS_ALIGN = 256;
+inline size_t ws_round(size_t b) { return (b + WS_ALIGN - 1) / WS_ALIGN * WS_ALIGN; }
+// image staging of the preprocessing entry points: sized by the caller's IMAGE, not by (batch, max_len, beam), so it
+// is not part of hmocr_workspace_bytes and always engine-owned (stream-ordered)
+inline bool ws_pool_exempt(const char* name) { return name[0] == 'p' && name[1] == 'p' && name[2] == '.'; }
+
 template <class T>
 int ws_get(hmocr_engine* e, const char* name, size_t count, T** out) {
+  const size_t bytes = ws_round(count * sizeof(T) + 1);
+  if (e->planning) {
+    size_t& need = e->plan[name];
+    if (need < bytes) need = bytes;
+    *out = reinterpret_cast<T*>(WS_ALIGN);      // never dereferenced: every schedule returns right after its ws_get calls
+    return 0;
+  }
   Buf& b = e->ws[name];
-  const size_t bytes = count * sizeof(T);
   if (b.cap < bytes) {
-    if (b.p != nullptr) {
-      HM_CUDA(cudaDeviceSynchronize());
-      HM_CUDA(cudaFree(b.p));
-      b.p = nullptr;
-      b.cap = 0;
+    if (e->ext_ws != nullptr && !ws_pool_exempt(name)) {
+      const size_t off = ws_round(e->ext_used);
+      auto pl = e->planned.find(name);
+      const size_t bytes_now = bytes;
+      const size_t bytes = (pl != e->planned.end() && pl->second > bytes_now) ? pl->second : bytes_now;
+      HM_CHECK(off + bytes <= e->ext_cap,
+               "caller-owned workspace too small for '%s' (%zu + %zu > %zu bytes): size it with hmocr_workspace_bytes for "
+               "the largest (batch, max_len, beam) you call with", name, off, bytes, e->ext_cap);
+      b.p = e->ext_ws + off;
+      b.cap = bytes;
+      e->ext_used = off + bytes;
+    } else {
+      if (b.p != nullptr) {
+        HM_CUDA(cudaFreeAsync(b.p, e->cur_stream));      // ordered after the kernels already enqueued on this stream
+        b.p = nullptr;
+        b.cap = 0;
+      }
+      const size_t want = ws_round(bytes + bytes / 8);
+      HM_CUDA(cudaMallocAsync(&b.p, want, e->cur_stream));
+      b.cap = want;
     }
-    const size_t want = bytes + bytes / 8 + 256;
-    HM_CUDA(cudaMalloc(&b.p, want));
-    b.cap = want;
     ++e->ws_epoch;
   }
   *out = reinterpret_cast<T*>(b.p);
@@ -275,8 +316,13 @@ int load_res18_weights(hmocr_engine* e) {
     cin = cout;
   }
   HM_TRY(upload_lin(e, "encoder.projection", d, 512, true, &e->r18_proj));
-  e->enc_layers.resize(c.num_layers);
-  for (int l = 0; l < c.num_layers; ++l) {
+  // config.res18trans_num_encoder_layers is independent of the decoder depth (src/config.py:28-29)
+  const int enc_layers = c.enc_num_layers > 0 ? c.enc_num_layers : c.num_layers;
+  HM_CHECK(find(e, "encoder.transformer_encoder.layers." + std::to_string(enc_layers) + ".linear1.weight") == nullptr,
+           "checkpoint has more than %d TransformerEncoder layers: set hmocr_config.enc_num_layers "
+           "(config.res18trans_num_encoder_layers)", enc_layers);
+  e->enc_layers.resize(enc_layers);
+  for (int l = 0; l < enc_layers; ++l) {
     const std::string p = "encoder.transformer_encoder.layers." + std::to_string(l) + ".";
     EncLayer& L = e->enc_layers[l];
     const HostTensor *w, *b;
@@ -313,6 +359,7 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* 
   HM_TRY(ws_get(e, "enc.qkv", tok1 * 288, &qkv));
   HM_TRY(ws_get(e, "enc.ctx", tok1 * 96, &ctx));
   HM_TRY(ws_get(e, "enc.hid", tok1 * 384, &hid));
+  if (e->planning) return 0;
 
   HM_TRY(patch_embed(st, images, B, e->pe_w, e->pe_b, e->pe_norm.g, e->pe_norm.b, xa));
   int H = 24, W = 80, C = 96, blk = 0;
@@ -376,7 +423,7 @@ int conv_gemm(hmocr_engine* e, cudaStream_t st, const h16* x16, int B, int H, in
 
 int encode_res18_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* enc16, cudaStream_t st) {
   const int d = e->cfg.d_model, ff = e->cfg.dim_feedforward, nh = e->cfg.nhead;
-  HM_CHECK(e->pos_table_set, "ResNet-18 variant: call hmocr_set_pos_table first - the reference draws a fresh "
+  HM_CHECK(e->planning || e->pos_table_set, "ResNet-18 variant: call hmocr_set_pos_table first - the reference draws a fresh "
                              "nn.Embedding(10, d_model) table on every encoder call (src/model_res18trans.py:57-59)");
   HM_CHECK(B <= 256, "ResNet-18 variant: the encoder attends ACROSS the batch (SURVEY.md D7); batch %d > 256 unsupported", B);
   const size_t m1 = (size_t)B * 24 * 80;                       // pixels after the stem
@@ -390,6 +437,17 @@ int encode_res18_impl(hmocr_engine* e, const float* images, int B, float* enc32,
   HM_TRY(ws_get(e, "r18.xb32", m1 * 64, &xb32));
   HM_TRY(ws_get(e, "r18.ds32", m1 * 64 / 2, &ds32));
   HM_TRY(ws_get(e, "r18.col", m1 * 576, &col));
+  const int S = RES18_MEM, rows = B * S;
+  h16 *pool16, *z16, *qkv, *ctx, *hid;
+  float *q32, *z32;
+  HM_TRY(ws_get(e, "r18.pool16", (size_t)rows * 512, &pool16));
+  HM_TRY(ws_get(e, "r18.q32", (size_t)rows * d, &q32));
+  HM_TRY(ws_get(e, "r18.z32", (size_t)rows * d, &z32));
+  HM_TRY(ws_get(e, "r18.z16", (size_t)rows * d, &z16));
+  HM_TRY(ws_get(e, "r18.qkv", (size_t)rows * 3 * d, &qkv));
+  HM_TRY(ws_get(e, "r18.ctx", (size_t)rows * d, &ctx));
+  HM_TRY(ws_get(e, "r18.hid", (size_t)rows * ff, &hid));
+  if (e->planning) return 0;
   HM_TRY(conv7x7_bn_relu(st, images, B, e->r18_w1, e->r18_b1, stem));
   HM_TRY(maxpool3x3s2(st, stem, B, 48, 160, 64, xa16, xa32));
   int H = 24, W = 80, C = 64;
@@ -420,16 +478,6 @@ int encode_res18_impl(hmocr_engine* e, const float* images, int B, float* enc32,
     }
   }
   // AdaptiveAvgPool2d((1, None)) -> Linear 512 -> d -> + positional table -> [10, B, d] -> 8 encoder layers over B
-  const int S = RES18_MEM, rows = B * S;
-  h16 *pool16, *z16, *qkv, *ctx, *hid;
-  float *q32, *z32;
-  HM_TRY(ws_get(e, "r18.pool16", (size_t)rows * 512, &pool16));
-  HM_TRY(ws_get(e, "r18.q32", (size_t)rows * d, &q32));
-  HM_TRY(ws_get(e, "r18.z32", (size_t)rows * d, &z32));
-  HM_TRY(ws_get(e, "r18.z16", (size_t)rows * d, &z16));
-  HM_TRY(ws_get(e, "r18.qkv", (size_t)rows * 3 * d, &qkv));
-  HM_TRY(ws_get(e, "r18.ctx", (size_t)rows * d, &ctx));
-  HM_TRY(ws_get(e, "r18.hid", (size_t)rows * ff, &hid));
   HM_TRY(avgpool_h(st, x32, B, H, W, C, pool16));
   GemmEpilogue ep;
   ep.out_f32 = q32; ep.ld32 = d;
@@ -523,6 +571,7 @@ int decoder_forward_impl(hmocr_engine* e, const float* enc32, const int64_t* tgt
   HM_TRY(ws_get(e, "tf.memkv", (size_t)B * e->mem_len * e->ca_kv.n, &memkv));
   DecBufs b;
   HM_TRY(dec_bufs(e, "tf", rows, &b));
+  if (e->planning) return 0;
   HM_TRY(f32_to_f16(st, enc32, (size_t)B * e->mem_len * d, enc16));
   HM_TRY(project_memory(e, enc16, B, memkv, st));
   HM_TRY(embed_tokens(st, tgt, T, B, T, e->emb, e->pos, d, e->cfg.vocab_size, b.x32, b.x16));
@@ -601,6 +650,7 @@ int generate_from_memory_impl(hmocr_engine* e, const h16* enc16, int B, int max_
   float* lp_ws;
   HM_TRY(ws_get(e, "gen.tokens", (size_t)rows * (g.tmax + 1), &tok_ws));
   HM_TRY(ws_get(e, "gen.logprob", (size_t)rows * g.tmax, &lp_ws));
+  if (e->planning) return 0;
 
   HM_TRY(project_memory(e, enc16, B, memkv, st));
   HM_TRY(init_decode(st, g.state, tok_ws, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, g.finished, lp_ws, max_len));
@@ -757,21 +807,37 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
     const size_t elems = set_elems * (beam_mode ? 2 : 1);
     uint64_t epoch = e->ws_epoch;
     HM_TRY(ws_get(e, "dp.kcache", elems, &kcache));
-    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(kcache, 0, e->ws["dp.kcache"].cap, st));
+    if (!e->planning && e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(kcache, 0, e->ws["dp.kcache"].cap, st));
     epoch = e->ws_epoch;
     HM_TRY(ws_get(e, "dp.vcache", elems, &vcache));
-    if (e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(vcache, 0, e->ws["dp.vcache"].cap, st));
+    if (!e->planning && e->ws_epoch != epoch) HM_CUDA(cudaMemsetAsync(vcache, 0, e->ws["dp.vcache"].cap, st));
   }
   HM_TRY(ws_get(e, "gen.state", 1, &state));
   HM_TRY(ws_get(e, "gen.finished", rows, &finished));
+  DecPersistParams p;
+  memset(&p, 0, sizeof(p));
+  if (beam_mode) {
+    HM_TRY(ws_get(e, "bm.score", rows, &p.bm_score));
+    HM_TRY(ws_get(e, "bm.fin", rows, &p.bm_fin));
+    HM_TRY(ws_get(e, "bm.src", rows, &p.bm_src));
+    HM_TRY(ws_get(e, "bm.tok", rows, &p.bm_tok));
+    HM_TRY(ws_get(e, "bm.parent", (size_t)max_len * rows, &p.bp_parent));
+    HM_TRY(ws_get(e, "bm.token", (size_t)max_len * rows, &p.bp_token));
+  }
+  if (e->trace_step >= 0) HM_TRY(ws_get(e, "gen.trace", 1024, &p.trace));
+  if (e->planning) return 0;
+  nvtx_push("hmocr.cross_kv");
   {
     GemmEpilogue ek;
     ek.out_f32 = memkv; ek.ld32 = e->ca_kv.n;
-    HM_TRY(run_lin(st, enc16, e->cfg.d_model, B * e->mem_len, e->ca_kv, ek));
+    const int rc = run_lin(st, enc16, e->cfg.d_model, B * e->mem_len, e->ca_kv, ek);
+    if (rc != 0) { nvtx_pop(); return rc; }
   }
-  HM_TRY(repack_memkv(st, memkv, B, L, e->mem_len, memk, memv));
-  DecPersistParams p;
-  memset(&p, 0, sizeof(p));
+  {
+    const int rc = repack_memkv(st, memkv, B, L, e->mem_len, memk, memv);
+    nvtx_pop();
+    HM_TRY(rc);
+  }
   p.wstream = e->dp_wstream;
   p.lnparams = e->dp_lnparams;
   p.emb = e->emb; p.pos = e->pos; p.kcache = kcache; p.vcache = vcache; p.memk = memk; p.memv = memv;
@@ -780,31 +846,29 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   p.chunks_per_step = e->dp_chunks_per_step;
   p.vocab = e->cfg.vocab_size; p.tmax = tmax; p.max_pos = e->cfg.max_seq_len; p.max_len = max_len;
   p.ld_tok = max_len + 1; p.eos = e->cfg.eos_id; p.pad = e->cfg.pad_id; p.cache_blocks = cache_blocks; p.mem_len = e->mem_len;
-  p.trace = nullptr; p.trace_step = e->trace_step; p.flags = e->dbg_flags;
+  p.trace_step = e->trace_step; p.flags = e->dbg_flags;
   p.rows_per_cluster = DP_ROWS;
   if (beam_mode) {
     p.rows_per_cluster = beam * (DP_ROWS / beam);
     p.cache_set_stride = set_elems;
-    HM_TRY(ws_get(e, "bm.score", rows, &p.bm_score));
-    HM_TRY(ws_get(e, "bm.fin", rows, &p.bm_fin));
-    HM_TRY(ws_get(e, "bm.src", rows, &p.bm_src));
-    HM_TRY(ws_get(e, "bm.tok", rows, &p.bm_tok));
-    HM_TRY(ws_get(e, "bm.parent", (size_t)max_len * rows, &p.bp_parent));
-    HM_TRY(ws_get(e, "bm.token", (size_t)max_len * rows, &p.bp_token));
     HM_TRY(beam_init(st, state, p.bm_score, p.bm_fin, p.bm_src, p.bm_tok, rows, beam, p.rows_per_cluster, e->cfg.sos_id));
   } else {
     HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   }
-  if (e->trace_step >= 0) {
-    HM_TRY(ws_get(e, "gen.trace", 1024, &p.trace));
-    HM_CUDA(cudaMemsetAsync(p.trace, 0, 1024 * sizeof(long long), st));
-  }
+  if (p.trace != nullptr) HM_CUDA(cudaMemsetAsync(p.trace, 0, 1024 * sizeof(long long), st));
   const int chunk = e->steps_per_launch > 0 ? e->steps_per_launch : 16;
   bool done = false;
   int poll_idx = 0;
   for (int s0 = 0; s0 < max_len && !done; s0 += chunk, ++poll_idx) {
     const int s1 = (s0 + chunk < max_len) ? s0 + chunk : max_len;
-    HM_TRY(decode_persistent_launch(st, p, s0, s1));
+    {
+      char tag[48];
+      snprintf(tag, sizeof(tag), "hmocr.decode launch %d [%d,%d)", poll_idx, s0, s1);
+      nvtx_push(tag);
+      const int rc = decode_persistent_launch(st, p, s0, s1);
+      nvtx_pop();
+      HM_TRY(rc);
+    }
     const int slot = poll_idx & 1;
     HM_CUDA(cudaMemcpyAsync(&e->pinned_state[slot], state, sizeof(DecodeState), cudaMemcpyDeviceToHost, st));
     HM_CUDA(cudaEventRecord(e->poll_ev[slot], st));
@@ -840,6 +904,7 @@ int encode_for_generate(hmocr_engine* e, const float* images, int B, float* enc3
   const size_t img_n = (size_t)B * IMG_H * IMG_W;
   float* stage;
   HM_TRY(ws_get(e, "gen.img_stage", img_n, &stage));
+  if (e->planning) return encode_any(e, images, B, enc32, enc16, st);
   hmocr_engine::EncGraph& eg = e->enc_graphs[B];
   if (!eg.warm) {                                   // first call: eager (everything gets allocated and initialised)
     eg.warm = true;
@@ -877,8 +942,15 @@ int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int 
   h16* enc16;
   HM_TRY(ws_get(e, "gen.enc32", (size_t)B * e->mem_len * e->cfg.d_model, &enc32));
   HM_TRY(ws_get(e, "gen.enc16", (size_t)B * e->mem_len * e->cfg.d_model, &enc16));
+  if (e->planning) {
+    HM_TRY(encode_for_generate(e, images, B, enc32, enc16, st));
+    return generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st);
+  }
   HM_CUDA(cudaEventRecord(e->ev[0], st));
-  HM_TRY(encode_for_generate(e, images, B, enc32, enc16, st));
+  nvtx_push("hmocr.encode");
+  const int rc_enc = encode_for_generate(e, images, B, enc32, enc16, st);
+  nvtx_pop();
+  HM_TRY(rc_enc);
   HM_CUDA(cudaEventRecord(e->ev[1], st));
   HM_TRY(generate_from_memory_impl(e, enc16, B, max_len, beam, tokens, logprob, steps, score, st));
   HM_CUDA(cudaEventRecord(e->ev[2], st));
@@ -886,12 +958,50 @@ int generate_impl(hmocr_engine* e, const float* images, int B, int max_len, int 
   return 0;
 }
 
-int check_ready(hmocr_engine* e, int B) {
+int check_ready(hmocr_engine* e, int B, void* stream) {
   HM_CHECK(e != nullptr, "null engine");
   HM_CHECK(e->finalized, "weights not loaded: call hmocr_load_weight for every entry, then hmocr_finalize_weights");
   HM_CHECK(B >= 1, "batch must be >= 1 (got %d)", B);
   HM_CUDA(cudaSetDevice(e->device));
+  e->cur_stream = static_cast<cudaStream_t>(stream);
   return 0;
+}
+
+// every scratch buffer a call with this shape asks for (the schedules run in planning mode: ws_get records, nothing launches)
+int plan_workspace(hmocr_engine* e, int B, int max_len, int beam, size_t* bytes) {
+  e->plan.clear();
+  e->planning = true;
+  int rc = 0;
+  float* fdummy = reinterpret_cast<float*>(WS_ALIGN);
+  int64_t* tdummy = reinterpret_cast<int64_t*>(WS_ALIGN);
+  if (beam == 0) {                                   // teacher-forced hmocr_decoder_forward(B, T = max_len)
+    rc = decoder_forward_impl(e, fdummy, tdummy, B, max_len, fdummy, nullptr);
+  } else {                                           // hmocr_encode + hmocr_generate* (device and host-buffer forms)
+    h16* d16;
+    uint8_t* u8;
+    float* f32;
+    int64_t* i64;
+    int32_t* i32;
+    const size_t img_n = (size_t)B * IMG_H * IMG_W;
+    rc = ws_get(e, "enc.out16", (size_t)B * e->mem_len * e->cfg.d_model, &d16);
+    if (rc == 0) rc = ws_get(e, "host.images_u8", img_n, &u8);
+    if (rc == 0) rc = ws_get(e, "host.images", img_n, &f32);
+    if (rc == 0) rc = ws_get(e, "host.tokens", (size_t)B * (max_len + 1), &i64);
+    if (rc == 0) rc = ws_get(e, "host.logprob", (size_t)B * max_len, &f32);
+    if (rc == 0) rc = ws_get(e, "host.steps", 1, &i32);
+    if (rc == 0) rc = ws_get(e, "host.score", B, &f32);
+    if (rc == 0) rc = generate_impl(e, fdummy, B, max_len, beam, tdummy, fdummy, nullptr, fdummy, nullptr);
+  }
+  e->planning = false;
+  for (auto& kv : e->plan) {
+    size_t& m = e->planned[kv.first];
+    if (m < kv.second) m = kv.second;
+  }
+  e->plan.clear();
+  size_t total = 0;
+  for (auto& kv : e->planned) total += kv.second;    // every entry is already rounded to WS_ALIGN
+  *bytes = total + WS_ALIGN;
+  return rc;
 }
 
 }  // namespace
@@ -911,6 +1021,7 @@ HM_API int hmocr_create(const hmocr_config* cfg, hmocr_engine** out) {
            cfg->d_model, cfg->nhead);
   HM_CHECK(cfg->dim_feedforward % 64 == 0 && cfg->dim_feedforward > 0, "dim_feedforward must be a multiple of 64");
   HM_CHECK(cfg->num_layers >= 1 && cfg->num_layers <= 32, "num_layers out of range");
+  HM_CHECK(cfg->enc_num_layers >= 0 && cfg->enc_num_layers <= 32, "enc_num_layers out of range");
   HM_CHECK(cfg->max_seq_len >= 2 && cfg->max_seq_len <= 256, "max_seq_len must be in [2,256]");
   HM_CHECK(cfg->vocab_size >= 4, "vocab_size too small");
   int ndev = 0;
@@ -940,8 +1051,11 @@ HM_API void hmocr_destroy(hmocr_engine* e) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto& kv : e->enc_graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  for (auto& kv : e->ws)
-    if (kv.second.p) cudaFree(kv.second.p);
+  for (auto& kv : e->ws) {
+    uint8_t* p = static_cast<uint8_t*>(kv.second.p);
+    const bool in_pool = e->ext_ws != nullptr && p >= e->ext_ws && p < e->ext_ws + e->ext_cap;   // the caller's memory
+    if (p != nullptr && !in_pool) cudaFree(p);
+  }
   if (e->arena) cudaFree(e->arena);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (int i = 0; i < 4; ++i)
@@ -974,10 +1088,22 @@ HM_API int hmocr_load_weight(hmocr_engine* e, const char* key, const void* data,
   return 0;
 }
 
+static int finalize_weights_impl(hmocr_engine* e);
+
 HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   HM_CHECK(e != nullptr, "null engine");
   HM_CHECK(!e->finalized, "weights already finalized");
   HM_CUDA(cudaSetDevice(e->device));
+  const int rc = finalize_weights_impl(e);
+  if (rc != 0 && e->arena != nullptr) {       // a failed load (missing / mis-shaped entry) must not leak the arena on retry
+    cudaFree(e->arena);
+    e->arena = nullptr;
+    e->arena_cap = e->arena_used = 0;
+  }
+  return rc;
+}
+
+static int finalize_weights_impl(hmocr_engine* e) {
   const hmocr_config& c = e->cfg;
   const int d = c.d_model, ff = c.dim_feedforward, V = c.vocab_size;
   size_t total = 0;
@@ -1073,13 +1199,41 @@ HM_API int hmocr_finalize_weights(hmocr_engine* e) {
   return 0;
 }
 
-HM_API int hmocr_set_pos_table(hmocr_engine* e, const float* pos_host, int rows, int d) {
+HM_API int hmocr_set_pos_table(hmocr_engine* e, const float* pos_host, int rows, int d, void* stream) {
   HM_CHECK(e != nullptr && pos_host != nullptr, "hmocr_set_pos_table: null argument");
   HM_CHECK(e->finalized && e->cfg.encoder_arch == 1, "hmocr_set_pos_table: only for a loaded ResNet-18 variant engine");
   HM_CHECK(rows == RES18_MEM && d == e->cfg.d_model, "positional table must be [%d, %d]", RES18_MEM, e->cfg.d_model);
   HM_CUDA(cudaSetDevice(e->device));
-  HM_CUDA(cudaMemcpy(e->pos_table, pos_host, sizeof(float) * rows * d, cudaMemcpyHostToDevice));
+  // stream-ordered: an encoder still running on this stream keeps reading the old table until it is done
+  HM_CUDA(cudaMemcpyAsync(e->pos_table, pos_host, sizeof(float) * rows * d, cudaMemcpyHostToDevice,
+                          static_cast<cudaStream_t>(stream)));
   e->pos_table_set = true;
+  return 0;
+}
+
+HM_API int hmocr_workspace_bytes(hmocr_engine* e, int batch, int max_len, int beam, size_t* bytes) {
+  HM_CHECK(e != nullptr && bytes != nullptr, "hmocr_workspace_bytes: null argument");
+  HM_CHECK(e->finalized, "hmocr_workspace_bytes: load the weights first (buffer sizes depend on the checkpoint's vocabulary)");
+  HM_CHECK(batch >= 1 && max_len >= 1 && beam >= 0, "hmocr_workspace_bytes: bad shape batch=%d max_len=%d beam=%d", batch, max_len, beam);
+  return plan_workspace(e, batch, max_len, beam, bytes);
+}
+
+HM_API int hmocr_set_workspace(hmocr_engine* e, void* workspace_dev, size_t bytes, void* stream) {
+  HM_CHECK(e != nullptr, "hmocr_set_workspace: null engine");
+  HM_CHECK(workspace_dev == nullptr || (reinterpret_cast<uintptr_t>(workspace_dev) % WS_ALIGN == 0 && bytes >= WS_ALIGN),
+           "hmocr_set_workspace: the buffer must be %zu-byte aligned and non-empty", WS_ALIGN);
+  HM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& kv : e->ws) {                     // engine-owned buffers go back to the pool, stream-ordered
+    uint8_t* p = static_cast<uint8_t*>(kv.second.p);
+    const bool in_pool = e->ext_ws != nullptr && p >= e->ext_ws && p < e->ext_ws + e->ext_cap;
+    if (p != nullptr && !in_pool) HM_CUDA(cudaFreeAsync(p, st));
+  }
+  e->ws.clear();
+  e->ext_ws = static_cast<uint8_t*>(workspace_dev);
+  e->ext_cap = workspace_dev ? bytes : 0;
+  e->ext_used = 0;
+  ++e->ws_epoch;                               // captured graphs hold the old addresses
   return 0;
 }
 
@@ -1126,7 +1280,7 @@ HM_API int hmocr_read_trace(hmocr_engine* e, int64_t* out_host, int n) {
 }
 
 HM_API int hmocr_encode(hmocr_engine* e, const float* images, int B, float* enc_out, void* stream) {
-  HM_TRY(check_ready(e, B));
+  HM_TRY(check_ready(e, B, stream));
   HM_CHECK(images != nullptr && enc_out != nullptr, "hmocr_encode: null buffer");
   h16* enc16;
   HM_TRY(ws_get(e, "enc.out16", (size_t)B * e->mem_len * e->cfg.d_model, &enc16));
@@ -1136,7 +1290,7 @@ HM_API int hmocr_encode(hmocr_engine* e, const float* images, int B, float* enc_
 
 HM_API int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out, const int64_t* tgt, int B, int T,
                                  float* logits, void* stream) {
-  HM_TRY(check_ready(e, B));
+  HM_TRY(check_ready(e, B, stream));
   HM_CHECK(enc_out != nullptr && tgt != nullptr && logits != nullptr, "hmocr_decoder_forward: null buffer");
   HM_CHECK(T >= 1 && T <= e->cfg.max_seq_len, "T=%d outside [1,%d] (tgt_mask / pos_encoder size)", T,
            e->cfg.max_seq_len);
@@ -1145,14 +1299,14 @@ HM_API int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out, const in
 
 HM_API int hmocr_generate(hmocr_engine* e, const float* images, int B, int max_len, int beam, int64_t* tokens,
                           float* logprob, int32_t* steps, float* score, void* stream) {
-  HM_TRY(check_ready(e, B));
+  HM_TRY(check_ready(e, B, stream));
   HM_CHECK(images != nullptr && tokens != nullptr, "hmocr_generate: null buffer");
   return generate_impl(e, images, B, max_len, beam, tokens, logprob, steps, score, static_cast<cudaStream_t>(stream));
 }
 
 HM_API int hmocr_generate_from_memory(hmocr_engine* e, const float* enc_out, int B, int max_len, int beam,
                                       int64_t* tokens, float* logprob, int32_t* steps, float* score, void* stream) {
-  HM_TRY(check_ready(e, B));
+  HM_TRY(check_ready(e, B, stream));
   HM_CHECK(enc_out != nullptr && tokens != nullptr, "hmocr_generate_from_memory: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   h16* enc16;
@@ -1169,7 +1323,7 @@ HM_API int hmocr_generate_from_memory(hmocr_engine* e, const float* enc_out, int
 HM_API int hmocr_generate_host(hmocr_engine* e, const float* images_host, int B, int max_len, int beam,
                                int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
                                void* stream) {
-  HM_TRY(check_ready(e, B));
+  HM_TRY(check_ready(e, B, stream));
   HM_CHECK(images_host != nullptr && tokens_host != nullptr, "hmocr_generate_host: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float *img_d, *lp_d, *score_d;
@@ -1199,6 +1353,7 @@ HM_API int hmocr_preprocess_image_u8(hmocr_engine* e, const uint8_t* image_host,
   HM_CHECK(height >= 1 && width >= 1 && height <= 16384 && width <= 16384, "hmocr_preprocess_image_u8: bad size %dx%d", height, width);
   HM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  e->cur_stream = st;
   uint8_t *src, *mid;
   int* tables;
   const size_t bytes = (size_t)height * width * channels;
@@ -1215,6 +1370,7 @@ HM_API int hmocr_preprocess_cv2_u8(hmocr_engine* e, const uint8_t* gray_host, in
   HM_CHECK(height >= 1 && width >= 1 && height <= 16384 && width <= 16384, "hmocr_preprocess_cv2_u8: bad size %dx%d", height, width);
   HM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  e->cur_stream = st;
   uint8_t* src;
   int* tables;
   const size_t bytes = (size_t)height * width;
@@ -1242,7 +1398,7 @@ HM_API int hmocr_preprocess_u8(hmocr_engine* e, const uint8_t* images_u8_dev, in
 HM_API int hmocr_generate_host_u8(hmocr_engine* e, const uint8_t* images_u8_host, int B, int max_len, int beam,
                                   int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
                                   void* stream) {
-  HM_TRY(check_ready(e, B));
+  HM_TRY(check_ready(e, B, stream));
   HM_CHECK(images_u8_host != nullptr && tokens_host != nullptr, "hmocr_generate_host_u8: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* u8_d;

@@ -623,7 +623,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
+int g_sms[HM_MAX_DEVICES] = {};      // per device: filled by gemm_init() on that device (0 = not initialised)
+int num_sms() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < HM_MAX_DEVICES && g_sms[dev] > 0) ? g_sms[dev] : 148;
+}
 std::mutex g_mu;
 std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
 
@@ -666,7 +671,7 @@ int launch(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16* 
   p.dbg = g_gemm_dbg;
   p.mode = epi.ln_gamma != nullptr ? EPI_LN
            : (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   HM_CUDA(launch_pdl(gemm_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, p));
   HM_LAUNCHED();
   return 0;
@@ -713,7 +718,7 @@ int launch_conv(cudaStream_t stream, const CUtensorMap& tmA, const h16* Wt, int 
   p.dbg = g_gemm_dbg;
   p.mode = (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
   p.cg = cg;
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   HM_CUDA(launch_pdl(gemm_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmA, tmB, p));
   HM_LAUNCHED();
   return 0;
@@ -733,7 +738,7 @@ int launch2(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16*
   p.dbg = g_gemm_dbg;
   p.mode = (epi.out_f32 == nullptr && epi.residual == nullptr && epi.act != 3) ? EPI_F16 : EPI_GENERAL;
   p.cg = ConvGeom{};
-  int pairs = g_num_sms / 2;
+  int pairs = num_sms() / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
@@ -795,7 +800,7 @@ int gemm_conv_f16(cudaStream_t stream, const h16* x, int B, int H, int W, int Ci
   for (int i = 0; i < 3; ++i) {
     if (N % cands[i] != 0) continue;
     bn = cands[i];
-    if (m_tiles * (N / cands[i]) >= g_num_sms) break;
+    if (m_tiles * (N / cands[i]) >= num_sms()) break;
   }
   HM_CHECK(bn != 0, "conv: output channels %d must be a multiple of 64", N);
   switch (bn) {
@@ -808,19 +813,21 @@ int gemm_conv_f16(cudaStream_t stream, const h16* x, int B, int H, int W, int Ci
 void gemm_set_debug(int v) { g_gemm_dbg = v; }
 
 int gemm_init() {
+  // per DEVICE: the shared-memory opt-in of a kernel is an attribute of the function on one device
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_encode != nullptr) return 0;
+  int cur = 0;
+  HM_CUDA(cudaGetDevice(&cur));
+  HM_CHECK(cur >= 0 && cur < HM_MAX_DEVICES, "device index %d", cur);
+  if (g_sms[cur] > 0) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   HM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
   HM_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
-  int dev = 0;
-  HM_CUDA(cudaGetDevice(&dev));
+  const int dev = cur;
   cudaDeviceProp prop;
   HM_CUDA(cudaGetDeviceProperties(&prop, dev));
   HM_CHECK(prop.major == 10, "libhmocr is built for sm_100a only; device is sm_%d%d (no fallback path)", prop.major,
            prop.minor);
-  g_num_sms = prop.multiProcessorCount;
   // set once, up front: nothing but launches may happen while a step graph is being captured
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<96>::SMEM_BYTES));
@@ -833,6 +840,7 @@ int gemm_init() {
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
   HM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  g_sms[dev] = prop.multiProcessorCount;
   return 0;
 }
 
@@ -862,7 +870,7 @@ int gemm_f16(cudaStream_t stream, const h16* A, int lda, int M, int K, const h16
     for (int i = 0; i < 5; ++i) {
       if (N % cands[i] != 0) continue;
       smallest = cands[i];
-      if (bn == 0 && mt * (N / cands[i]) >= g_num_sms) bn = cands[i];
+      if (bn == 0 && mt * (N / cands[i]) >= num_sms()) bn = cands[i];
     }
     if (bn == 0) bn = smallest;
     HM_CHECK(bn != 0, "gemm: N=%d is not a multiple of 64 or 96", N);

@@ -19,7 +19,10 @@ struct DecodeState {      // device-resident control block of one generate call
   int step;               // current decode step t (position of the token being fed)
   int finished_count;     // rows that have emitted eos at least once
   int steps_executed;     // ys.shape[1]-1 of the reference once every row has finished, else 0
-  int pad_;
+  int last_eos;           // max over the finished rows (beam: clusters) of (step of the first eos) + 1.  Clusters of the
+                          // persistent kernel run their step range independently (and in waves), so the row that
+                          // finishes LAST in time is not the row that finishes at the LATEST step: steps_executed is
+                          // published from this maximum, never from the publishing thread's own step.
 };
 
 // x[r] = embedding[tok[b, t]] + pos[t]  for r = b*T + t   (src/model_swin.py:73-75)

@@ -352,12 +352,8 @@ int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, con
   HM_CHECK(C % 8 == 0, "window_attention: C must be a multiple of 8");
   const int Hp = ceil_div(H, WS) * WS, Wp = ceil_div(W, WS) * WS;
   const int sh = (Hp > WS) ? shift : 0, sw = (Wp > WS) ? shift : 0;   // swin_transformer.py:158-163
-  static bool attr = false;
   const int smem = (int)sizeof(CtaShared);
-  if (!attr) {
-    HM_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  HM_DEVICE_ONCE(HM_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
   // CTAs are bound to heads (block % heads): 2 CTAs per SM (105 KB each), rounded down to a multiple of heads;
   // fewer when there are not enough windows to give every warp one.
   const long windows = (long)B * (Hp / WS) * (Wp / WS);
@@ -375,11 +371,7 @@ int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, con
 // qkv fp16 [B*T, 3*nhead*32] (row = b*T + t) -> ctx fp16 [B*T, nhead*32]; T <= 256
 int mha_full_mma(cudaStream_t st, const h16* qkv, int B, int T, int nhead, h16* ctx) {
   HM_CHECK(T >= 1 && T <= FA_MAXT, "mha_full_mma: T=%d out of range", T);
-  static bool attr = false;
-  if (!attr) {
-    HM_CUDA(cudaFuncSetAttribute(full_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullAttnSmem)));
-    attr = true;
-  }
+  HM_DEVICE_ONCE(HM_CUDA(cudaFuncSetAttribute(full_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullAttnSmem))));
   HM_CUDA(launch_pdl(full_attn_mma_kernel, dim3(B * nhead), dim3(FA_WARPS * 32), sizeof(FullAttnSmem), st, qkv, T, nhead, ctx));
   HM_LAUNCHED();
   return 0;

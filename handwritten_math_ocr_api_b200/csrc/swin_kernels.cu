@@ -302,11 +302,7 @@ int patch_merge_ln(cudaStream_t st, const float* x, int B, int H, int W, int Cin
 int patch_embed(cudaStream_t st, const float* images, int B, const float* w, const float* b, const float* g,
                 const float* beta, float* x) {
   const int ntok = B * 24 * 80;
-  static bool attr = false;
-  if (!attr) {
-    HM_CUDA(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PatchSmem)));
-    attr = true;
-  }
+  HM_DEVICE_ONCE(HM_CUDA(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PatchSmem))));
   int blocks = ceil_div(ntok / 32, PE_WARPS);
   if (blocks > 148 * 3) blocks = 148 * 3;
   HM_CUDA(launch_pdl(patch_embed_kernel, dim3(blocks), dim3(PE_WARPS * 32), sizeof(PatchSmem), st, images, ntok, w, b, g, beta, x));

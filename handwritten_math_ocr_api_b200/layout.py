@@ -118,7 +118,7 @@ def _bn_keys(p: str, c: int):
             (p + ".running_var", (c,), f32), (p + ".num_batches_tracked", (), "int64")]
 
 
-def state_dict_layout_res18(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
+def state_dict_layout_res18(cfg: ModelConfig, enc_layers: int = 0) -> List[Tuple[str, Tuple[int, ...], str]]:
     """The 367 (name, shape, dtype) entries of model_res18trans.FormulaRecognitionModel(V).state_dict()
     in the reference's own order (checked against the live reference by oracle/make_golden_res18.py)."""
     f32 = "float32"
@@ -136,7 +136,7 @@ def state_dict_layout_res18(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...]
         cin = c
     d, ff, v = cfg.d_model, cfg.dim_feedforward, cfg.vocab_size
     out += [("encoder.projection.weight", (d, 512), f32), ("encoder.projection.bias", (d,), f32)]
-    for l in range(cfg.num_layers):
+    for l in range(enc_layers or cfg.num_layers):        # config.res18trans_num_encoder_layers (src/config.py:28)
         p = f"encoder.transformer_encoder.layers.{l}."
         out += [(p + "self_attn.in_proj_weight", (3 * d, d), f32), (p + "self_attn.in_proj_bias", (3 * d,), f32),
                 (p + "self_attn.out_proj.weight", (d, d), f32), (p + "self_attn.out_proj.bias", (d,), f32),

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .layout import RES18_MEM_TOKENS
-from .model_swin import DecoderTransformer, FormulaRecognitionModel as _Base, _ptr
+from .model_swin import DecoderTransformer, FormulaRecognitionModel as _Base, _ptr, _stream
 
 
 class EncoderCNN:
@@ -43,6 +43,7 @@ class FormulaRecognitionModel(_Base):
     ENCODER_ARCH = 1
     MEM_TOKENS = RES18_MEM_TOKENS
     DECODER_LAYERS_ATTR = ("res18trans_num_decoder_layers", "num_decoder_layers")
+    ENCODER_LAYERS_ATTR = ("res18trans_num_encoder_layers",)      # src/config.py:28 (independent of the decoder depth)
 
     def __init__(self, vocab_size: int, config=None, device=None, **kw):
         super().__init__(vocab_size, config=config, device=device, **kw)
@@ -62,8 +63,8 @@ class FormulaRecognitionModel(_Base):
         if tuple(t.shape) != (self.mem_tokens, self.d_model):
             raise ValueError(f"pos_table must be [{self.mem_tokens}, {self.d_model}], got {tuple(t.shape)}")
         with torch.cuda.device(self.device):
-            _lib.check(self._eng.lib.hmocr_set_pos_table(self._handle(), C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1]),
-                       "hmocr_set_pos_table")
+            _lib.check(self._eng.lib.hmocr_set_pos_table(self._handle(), C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1],
+                                                         _stream()), "hmocr_set_pos_table")
         self.last_pos_table = t
         return t
 

@@ -94,6 +94,7 @@ class DecoderTransformer:
             raise ValueError(f"T={T} exceeds max_seq_len={m.max_seq_len} (pos_encoder / tgt_mask size)")
         if int(tgt.min()) < 0 or int(tgt.max()) >= m.vocab_size:
             raise IndexError("index out of range in self")         # what nn.Embedding raises
+        m._reserve("tf", B, T)
         out = torch.empty(B, T, m.vocab_size, dtype=torch.float32, device=m.device)
         with torch.cuda.device(m.device):
             _lib.check(m._eng.lib.hmocr_decoder_forward(m._handle(), _ptr(enc), _ptr(tgt), B, T, _ptr(out), _stream()),
@@ -112,6 +113,7 @@ class FormulaRecognitionModel:
     ENCODER_ARCH = 0          # hmocr_config.encoder_arch: 0 = Swin-T
     MEM_TOKENS = MEM_TOKENS   # memory tokens per image the encoder produces
     DECODER_LAYERS_ATTR = ("swin_num_decoder_layers", "num_decoder_layers")
+    ENCODER_LAYERS_ATTR = ()  # only the ResNet-18 variant has TransformerEncoder layers
 
     def __init__(self, vocab_size: int, config=None, device=None, drop_last_caption: bool = False,
                  sos_id: int = 1, eos_id: int = 2, pad_id: int = 0):
@@ -134,10 +136,19 @@ class FormulaRecognitionModel:
                 break
         self.drop_last_caption = drop_last_caption
         self.sos_id, self.eos_id, self.pad_id = sos_id, eos_id, pad_id
+        enc_layers = 0
+        for attr in self.ENCODER_LAYERS_ATTR:
+            if hasattr(cfg, attr):
+                enc_layers = int(getattr(cfg, attr))
+                break
+        self.enc_num_layers = enc_layers
         c = _lib.HmocrConfig(self.vocab_size, self.d_model, int(cfg.nhead), int(cfg.dim_feedforward), self.num_layers,
-                             self.max_seq_len, sos_id, eos_id, pad_id, self.ENCODER_ARCH)
+                             self.max_seq_len, sos_id, eos_id, pad_id, self.ENCODER_ARCH, enc_layers)
         self._eng = _Engine(c, self.device)
         self._n_params = 0
+        # scratch memory is a torch tensor handed to the engine (SURVEY.md 8b "Ownership"): see _reserve
+        self._workspace: Optional[torch.Tensor] = None
+        self._reserved = {"gen": (0, 0, 0), "tf": (0, 0)}
         self.encoder = EncoderSwin(self)
         self.decoder = DecoderTransformer(self)
         self.training = False
@@ -174,12 +185,36 @@ class FormulaRecognitionModel:
         """Only used by the reference for a parameter count (app/src/main.py:672)."""
         yield torch.empty(self._n_params, device="meta")
 
+    def expected_keys(self):
+        """Names of the reference module's ``state_dict()`` for this configuration (layout.py)."""
+        from .layout import ModelConfig, state_dict_layout, state_dict_layout_res18
+        mc = ModelConfig(vocab_size=self.vocab_size, max_seq_len=self.max_seq_len, num_layers=self.num_layers)
+        if self.ENCODER_ARCH == 1:
+            return [name for name, _, _ in state_dict_layout_res18(mc, self.enc_num_layers)]
+        return [name for name, _, _ in state_dict_layout(mc)]
+
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
-        """Accepts the reference's 517-entry layout (or ``{'model_state_dict': ...}``)."""
+        """Accepts the reference's 517-entry layout (or ``{'model_state_dict': ...}``).
+
+        ``strict=True`` (the nn.Module default the reference uses, src/predict.py:29): a key the reference module
+        does not have, or a missing one, raises ``RuntimeError`` like ``nn.Module.load_state_dict``;
+        ``strict=False`` reports them in the returned ``_IncompatibleKeys``.  Either way the engine itself refuses to
+        finalise when an entry it needs is absent or mis-shaped."""
         if "model_state_dict" in state_dict and not any(k.startswith("encoder.") for k in state_dict):
             state_dict = state_dict["model_state_dict"]        # src/utils.py:61-71 checkpoint dict
         if self._eng.loaded:
             raise RuntimeError("weights already loaded into this engine; construct a new model to reload")
+        missing, unexpected = [], []
+        try:
+            want = set(self.expected_keys())
+            missing = sorted(want - set(state_dict))
+            unexpected = sorted(set(state_dict) - want)
+        except Exception:                                      # a configuration layout.py cannot describe: engine checks only
+            pass
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict for FormulaRecognitionModel: "
+                               f"missing keys {missing[:8]}{'...' if len(missing) > 8 else ''}, "
+                               f"unexpected keys {unexpected[:8]}{'...' if len(unexpected) > 8 else ''}")
         lib, h = self._eng.lib, self._eng.handle
         n_params = 0
         keep = []
@@ -200,7 +235,7 @@ class FormulaRecognitionModel:
             _lib.check(lib.hmocr_finalize_weights(h), "hmocr_finalize_weights")
         self._n_params = n_params
         self._eng.loaded = True
-        return torch.nn.modules.module._IncompatibleKeys([], [])
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     @staticmethod
     def _counts_as_parameter(key: str) -> bool:
@@ -217,9 +252,39 @@ class FormulaRecognitionModel:
         m.load_state_dict(sd)
         return m
 
+    # ---- scratch memory ------------------------------------------------------------------------------
+    def _reserve(self, kind: str, *shape: int) -> None:
+        """Make the caller-owned workspace large enough for a call of this shape.
+
+        ``kind='gen'``: ``(batch, max_len, beam)`` of encoder / generate calls; ``kind='tf'``: ``(batch, T)`` of the
+        teacher-forced decoder.  The buffer is ONE uint8 torch tensor (torch's caching allocator, current stream) sized
+        by ``hmocr_workspace_bytes`` for the largest shapes seen so far and handed over with ``hmocr_set_workspace``;
+        the engine allocates nothing itself.  Growing re-places every buffer (rare: shapes only ever grow)."""
+        have = self._reserved[kind]
+        if all(a >= b for a, b in zip(have, shape)):
+            return
+        self._reserved[kind] = tuple(max(a, b) for a, b in zip(have, shape))
+        lib, h = self._eng.lib, self._handle()
+        n = C.c_size_t()
+        with torch.cuda.device(self.device):
+            # the engine keeps the per-buffer maximum over every shape asked so far: `n` covers all of them
+            if kind == "gen":
+                b, t, k = self._reserved["gen"]
+                _lib.check(lib.hmocr_workspace_bytes(h, b, t, k, C.byref(n)), "hmocr_workspace_bytes")
+            else:
+                b, t = self._reserved["tf"]
+                _lib.check(lib.hmocr_workspace_bytes(h, b, t, 0, C.byref(n)), "hmocr_workspace_bytes")
+            ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.hmocr_set_workspace(h, _ptr(ws), n.value, _stream()), "hmocr_set_workspace")
+        self._workspace = ws                                     # the old tensor goes back to torch's allocator
+
+    def workspace_bytes(self) -> int:
+        return 0 if self._workspace is None else self._workspace.numel()
+
     # ---- forward ------------------------------------------------------------------------------------
     def _encoder_call(self, x: torch.Tensor) -> torch.Tensor:
         x = self._images(x)
+        self._reserve("gen", x.shape[0], 1, 1)
         out = torch.empty(x.shape[0], self.mem_tokens, self.d_model, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._eng.lib.hmocr_encode(self._handle(), _ptr(x), x.shape[0], _ptr(out), _stream()), "hmocr_encode")
@@ -233,6 +298,13 @@ class FormulaRecognitionModel:
             raise ValueError("empty batch")
         return x
 
+    def _memory(self, encoder_out: torch.Tensor) -> torch.Tensor:
+        """Encoder output handed back by the caller: must be ``[B, mem_tokens, d_model]`` (the kernels index it raw)."""
+        x = encoder_out.to(device=self.device, dtype=torch.float32).contiguous()
+        if x.dim() != 3 or x.shape[0] < 1 or tuple(x.shape[1:]) != (self.mem_tokens, self.d_model):
+            raise ValueError(f"encoder_out must be [B>=1,{self.mem_tokens},{self.d_model}], got {tuple(x.shape)}")
+        return x
+
     def forward(self, images: torch.Tensor, captions: torch.Tensor) -> torch.Tensor:
         feats = self.encoder(images)
         return self.decoder(feats, captions[:, :-1] if self.drop_last_caption else captions)
@@ -242,23 +314,30 @@ class FormulaRecognitionModel:
     # ---- the fast path ---------------------------------------------------------------------------
     @torch.no_grad()
     def generate_device(self, images: Optional[torch.Tensor] = None, max_len: Optional[int] = None,
-                        return_logprobs: bool = False, encoder_out: Optional[torch.Tensor] = None):
+                        return_logprobs: bool = False, encoder_out: Optional[torch.Tensor] = None, beam_size: int = 1):
         """``generate`` without the host synchronisation: everything stays on the stream.
 
-        Returns ``(tokens int64 [B, 1+max_len], steps int32 [1] (device), logprobs f32 [B, max_len] | None)``;
-        columns past ``steps`` hold ``pad``.  Used where the result feeds another stream-ordered operation
-        (the multi-GPU token gather) so the GPU never idles waiting for the host."""
+        Returns ``(tokens int64 [B, 1+max_len], steps int32 [1] (device), logprobs f32 [B, max_len] | None)``
+        (``beam_size > 1``: the 4th element is the best hypothesis' score, f32 ``[B]``); columns past ``steps`` hold
+        ``pad``.  Used where the result feeds another stream-ordered operation (the multi-GPU token gather, a pipelined
+        device-to-host copy) so the GPU never idles waiting for the host."""
         max_len = int(max_len if max_len is not None else self.max_seq_len)
         lib = self._eng.lib
-        x = self._images(images) if encoder_out is None else encoder_out.to(device=self.device, dtype=torch.float32).contiguous()
+        x = self._images(images) if encoder_out is None else self._memory(encoder_out)
         B = x.shape[0]
+        if not 1 <= max_len <= self.max_seq_len:
+            raise RuntimeError(f"max_len={max_len} outside [1, {self.max_seq_len}] (size of pos_encoder, src/model_swin.py:54)")
+        self._reserve("gen", B, max_len, int(beam_size))
         tokens = torch.empty(B, max_len + 1, dtype=torch.int64, device=self.device)
         logp = torch.empty(B, max_len, dtype=torch.float32, device=self.device) if return_logprobs else None
         steps = torch.zeros(1, dtype=torch.int32, device=self.device)
+        score = torch.zeros(B, dtype=torch.float32, device=self.device) if beam_size > 1 else None
         with torch.cuda.device(self.device):
             fn = lib.hmocr_generate if encoder_out is None else lib.hmocr_generate_from_memory
-            _lib.check(fn(self._handle(), _ptr(x), B, max_len, 1, _ptr(tokens), _ptr(logp), _ptr(steps), None, _stream()),
-                       "hmocr_generate")
+            _lib.check(fn(self._handle(), _ptr(x), B, max_len, int(beam_size), _ptr(tokens), _ptr(logp), _ptr(steps),
+                          _ptr(score), _stream()), "hmocr_generate")
+        if beam_size > 1:
+            return tokens, steps, logp, score
         return tokens, steps, logp
 
     @torch.no_grad()
@@ -272,12 +351,11 @@ class FormulaRecognitionModel:
         """
         max_len = int(max_len if max_len is not None else self.max_seq_len)
         lib = self._eng.lib
-        if encoder_out is None:
-            x = self._images(images)
-            B = x.shape[0]
-        else:
-            x = encoder_out.to(device=self.device, dtype=torch.float32).contiguous()
-            B = x.shape[0]
+        x = self._images(images) if encoder_out is None else self._memory(encoder_out)
+        B = x.shape[0]
+        if not 1 <= max_len <= self.max_seq_len:
+            raise RuntimeError(f"max_len={max_len} outside [1, {self.max_seq_len}] (size of pos_encoder, src/model_swin.py:54)")
+        self._reserve("gen", B, max_len, int(beam_size))
         tokens = torch.empty(B, max_len + 1, dtype=torch.int64, device=self.device)
         logp = torch.empty(B, max_len, dtype=torch.float32, device=self.device) if return_logprobs else None
         steps = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -309,6 +387,8 @@ class FormulaRecognitionModel:
     def set_option(self, name: str, value: int) -> None:
         """Engine options of ``hmocr_set_option`` (``decode_impl``, ``steps_per_launch``)."""
         _lib.check(self._eng.lib.hmocr_set_option(self._eng.handle, name.encode(), int(value)), "hmocr_set_option")
+        # options change which scratch buffers a call uses (step graph / beam kernel / tracing): plan again
+        self._reserved = {"gen": (0, 0, 0), "tf": (0, 0)}
 
     def last_timings_ms(self) -> Tuple[float, float]:
         enc, dec = C.c_float(), C.c_float()

@@ -56,8 +56,13 @@ def gather_tokens_device(tokens_full: torch.Tensor, steps: torch.Tensor, group=N
     out = torch.empty(world * tokens_full.shape[0], tokens_full.shape[1], dtype=tokens_full.dtype,
                       device=tokens_full.device)
     all_steps = torch.empty(world, dtype=steps.dtype, device=steps.device)
+    nvtx = tokens_full.is_cuda
+    if nvtx:
+        torch.cuda.nvtx.range_push("hmocr.gather_tokens")        # NVTX range per phase
     dist.all_gather_into_tensor(out, tokens_full.contiguous(), group=group)
     dist.all_gather_into_tensor(all_steps, steps, group=group)
+    if nvtx:
+        torch.cuda.nvtx.range_pop()
     return out, all_steps
 
 

@@ -65,8 +65,8 @@ def preprocess_batch_gpu(model, images) -> torch.Tensor:
     bit-identical to ``torch.cat([preprocess_image(i) for i in images])``."""
     arrs = [_as_u8_array(i) for i in images]
     out = torch.empty(len(arrs), 1, config.img_h, config.img_w, dtype=torch.float32, device=model.device)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     with torch.cuda.device(model.device):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)      # the current stream OF the model's device
         for b, a in enumerate(arrs):
             _lib.check(model._eng.lib.hmocr_preprocess_image_u8(model._handle(), C.c_void_p(a.ctypes.data),
                                                                 1 if a.ndim == 2 else 3, a.shape[0], a.shape[1],
@@ -87,8 +87,8 @@ def preprocess_dataloader_gpu(model, grays) -> torch.Tensor:
     if any(a.ndim != 2 for a in arrs):
         raise ValueError("the loader reads images with cv2.IMREAD_GRAYSCALE: uint8 [H,W] arrays expected")
     out = torch.empty(len(arrs), 1, config.img_h, config.img_w, dtype=torch.float32, device=model.device)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     with torch.cuda.device(model.device):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)      # the current stream OF the model's device
         for b, a in enumerate(arrs):
             _lib.check(model._eng.lib.hmocr_preprocess_cv2_u8(model._handle(), C.c_void_p(a.ctypes.data), a.shape[0],
                                                               a.shape[1], C.c_void_p(out[b].data_ptr()), stream),

@@ -13,7 +13,10 @@
  *   - pointers named *_dev are CUDA device pointers owned by the caller (torch tensors on the
  *     Python side); *_host are host pointers.  `stream` is a cudaStream_t passed as void*.
  *     All work is enqueued on that stream; only the *_host entry points synchronise.
- *   - the engine owns its weights and scratch buffers (allocated at load / first use).
+ *   - the engine owns its weights (one arena, allocated by hmocr_finalize_weights).  Scratch memory is the CALLER's
+ *     when hmocr_set_workspace has been called (one buffer sized by hmocr_workspace_bytes - a torch tensor on the
+ *     Python side - inside which the engine places its named buffers; it then allocates nothing); otherwise the
+ *     engine takes scratch from the CUDA stream-ordered allocator on the caller's stream (no device-wide sync).
  *   - one engine = one CUDA device (current device at hmocr_create); not thread-safe per handle.
  */
 #ifndef HMOCR_H_
@@ -40,6 +43,8 @@ typedef struct hmocr_config {
   int32_t sos_id, eos_id, pad_id; /* vocab['<sos>'], vocab['<eos>'], vocab['<pad>'] = 1, 2, 0  */
   int32_t encoder_arch;    /* 0 = Swin-T (src/model_swin.py, 30 memory tokens);
                               1 = ResNet-18 + TransformerEncoder (src/model_res18trans.py, 10 memory tokens) */
+  int32_t enc_num_layers;  /* encoder_arch 1: config.res18trans_num_encoder_layers (src/config.py:28);
+                              0 = same as num_layers                                              */
 } hmocr_config;
 
 enum { HMOCR_F32 = 0, HMOCR_I64 = 1 };
@@ -81,7 +86,22 @@ int hmocr_read_trace(hmocr_engine* e, int64_t* out_host, int n);
 /* ResNet-18 variant only: the positional table added to the 10 pooled tokens.  The reference creates a fresh
  * N(0,1)-initialised nn.Embedding(10, d_model) on EVERY encoder call (src/model_res18trans.py:57-59), so the
  * table is an input here: pos_host f32 [10, d_model].  Used by the following hmocr_encode / hmocr_generate calls. */
-int hmocr_set_pos_table(hmocr_engine* e, const float* pos_host, int rows, int d);
+int hmocr_set_pos_table(hmocr_engine* e, const float* pos_host, int rows, int d, void* stream);
+
+/* Scratch memory owned by the caller (SURVEY.md section 8b "Ownership"; the reference has no counterpart - its
+ * activations live in torch's caching allocator, which is where this buffer comes from on the Python side).
+ *   hmocr_workspace_bytes: bytes of scratch that hmocr_encode + hmocr_generate* (device and host-buffer forms) need
+ *     for `batch` images, `max_len` steps and `beam` hypotheses with the engine's current options; beam == 0 asks for
+ *     the teacher-forced hmocr_decoder_forward(batch, T = max_len) instead.  The engine remembers the per-buffer
+ *     maximum over all shapes asked so far, and *bytes covers ALL of them (ask once per shape you will use, pass the
+ *     last answer to hmocr_set_workspace).
+ *   hmocr_set_workspace: hand the engine one device buffer (256-byte aligned).  It stays the caller's; it must
+ *     outlive every call that uses it; calling again (larger buffer) or with NULL (back to engine-owned scratch)
+ *     drops all placements - stream-ordered on `stream`.  A call whose buffers do not fit fails with a message
+ *     naming the buffer; nothing is allocated behind the caller's back.  The image staging of
+ *     hmocr_preprocess_image_u8 / _cv2_u8 is sized by the image, not by (batch, max_len, beam): always engine-owned. */
+int hmocr_workspace_bytes(hmocr_engine* e, int batch, int max_len, int beam, size_t* bytes);
+int hmocr_set_workspace(hmocr_engine* e, void* workspace_dev, size_t bytes, void* stream);
 
 /* How many 8-CTA decode clusters (16 sequences each) can be co-resident on the current device. */
 int hmocr_decode_max_clusters(int* out);
@@ -103,7 +123,7 @@ int hmocr_decoder_forward(hmocr_engine* e, const float* enc_out_dev, const int64
  *   steps_dev    int32 [1]             number of decode steps executed = ys.shape[1]-1 of the
  *                                      reference (stops when every row has emitted eos)
  * beam == 1: greedy, finished rows keep decoding exactly as the reference does.
- * beam  > 1: beam search (2..5 hypotheses per image) as defined in DESIGN.md section 4.6 - the reference
+ * beam  > 1: beam search (2..5 hypotheses per image) as defined in DESIGN.md section 4.5 - the reference
  *            has none, `beam_size` is an unused parameter of src/inference.py:7; tokens are the best
  *            hypothesis per image (finished hypotheses are padded), score_dev f32 [B] its summed
  *            log-probability (may be NULL); logprob_dev is zero-filled. */

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--flags", type=int, nargs="*", default=[0, 1, 3, 7])
     ap.add_argument("--only", default="", help="substring filter on the gemm name (for an ncu capture)")
+    ap.add_argument("--ncu", action="store_true", help="ONE launch per shape after one warm-up (for an ncu metrics pass; "
+                                                       "prints the launch order so the csv rows can be named)")
     a = ap.parse_args()
     cfg = ModelConfig()
     m = FormulaRecognitionModel(cfg.vocab_size)
@@ -62,6 +64,15 @@ def main():
         floor = nbytes / HBM * 1e6
         floor_total += floor
         line = f"{name:16s} {M:7d} {K:5d} {N:5d} {floor:9.1f} "
+        if a.ncu:
+            def run1():
+                rc = lib.hmocr_gemm_f16(P(A), K, M, K, P(W), N, P(bias), act, P(R), N if res else 0, P(o32), N, P(o16), N,
+                                        None, None, a.bn, st)
+                _lib.check(rc, "gemm")
+            run1(); run1()
+            torch.cuda.synchronize()
+            print(f"NCU_ORDER {name}|{M}|{K}|{N}|{2.0 * M * K * N:.0f}")
+            continue
         for f in a.flags:
             m.set_option("gemm_dbg", f)
 

@@ -21,6 +21,17 @@ def short(name):
     return name.replace("void hmocr::<unnamed>::", "").replace("hmocr::<unnamed>::", "")
 
 
+def kernel_source_sha():
+    """Hash of the decode kernel's sources at capture time: bench.py prints `roofline.traffic` from decode_traffic.json
+    only while the library it runs was built from the same sources."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(os.path.dirname(HERE), "handwritten_math_ocr_api_b200", "csrc")
+    for f in ("decode_persistent.cu", "decode_persistent.cuh"):
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()
+
+
 def launches(path, tag, batch=256, max_len=150):
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
@@ -55,6 +66,7 @@ def launches(path, tag, batch=256, max_len=150):
         a[0] += 1
         a[1] += e["gpu__time_duration.sum"]
     summary = {"batch": batch, "max_len": max_len, "source": os.path.basename(path),
+               "kernel_source_sha256": kernel_source_sha(),
                "decode_kernel_launches": len(dec), "decode_kernel_time_us_under_ncu": t_dec,
                "dram_bytes_per_step": traffic, "step_time_us_under_ncu": tot,
                "decode_kernel_share_of_step": t_dec / tot,

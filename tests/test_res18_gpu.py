@@ -3,8 +3,8 @@
 (oracle/make_golden_res18.py) and against the oracle on the same inputs.
 
 Tolerances (fp16 operands, fp32 accumulation; trunk activations reach ~330 with the synthetic He-scaled
-checkpoint, encoder features have std ~1.0): features max-abs <= 2e-2, teacher-forced logits <= 3e-2,
-greedy tokens identical or diverging at a reference margin < 6e-2.
+checkpoint, encoder features have std ~1.0): features max-abs <= 1.5e-2 (measured 1.0e-2), teacher-forced logits
+<= 1e-2 (north_star's figure; measured 7.7e-3), greedy tokens identical or diverging at a reference margin < 2e-2.
 """
 import os
 
@@ -14,8 +14,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-FEAT_TOL = 2e-2
-LOGIT_TOL = 3e-2
+FEAT_TOL = 1.5e-2
+LOGIT_TOL = 1e-2
 
 
 @pytest.fixture(scope="module")
@@ -98,11 +98,33 @@ def test_greedy_generate_against_reference_golden(rmodel, gold, cfg):
     print(f"res18 identical greedy sequences: {same}/4, steps {steps} (reference {ref.shape[1] - 1})")
 
 
-def test_beam_search_runs_on_the_variant(rmodel, gold):
+def test_beam_search_on_the_variant_scores_like_the_oracle(rmodel, rsd, gold, cfg):
+    """Beam 3 through the 10-token memory: the reported score is the oracle's log-probability of the returned
+    sequence (scoring + back-track), and it is never worse than the greedy sequence's."""
+    from oracle import res18_model as R
     pos = torch.from_numpy(gold["pos_table"])
-    tokens, steps, _, score = rmodel.generate(_imgs(gold).cuda(), max_len=20, beam_size=3, pos_table=pos)
-    g_tok, _, g_lp = rmodel.generate(_imgs(gold).cuda(), max_len=20, return_logprobs=True, pos_table=pos)
-    assert tokens.shape[0] == 4 and torch.isfinite(score).all()
+    imgs = _imgs(gold).cuda()
+    feats = rmodel.encoder(imgs, pos)
+    tokens, steps, _, score = rmodel.generate(encoder_out=feats, max_len=20, beam_size=3)
+    g_tok, _, g_lp = rmodel.generate(encoder_out=feats, max_len=20, return_logprobs=True)
+    assert tokens.shape == (4, steps + 1) and torch.isfinite(score).all()
+
+    def oracle_score(tok):
+        with torch.no_grad():
+            lsm = torch.log_softmax(R.decoder_forward(feats.cpu(), tok[:, :-1].cpu(), rsd, cfg).float(), -1)
+        out = []
+        for r in range(tok.shape[0]):
+            s = 0.0
+            for t in range(1, tok.shape[1]):
+                tk = int(tok[r, t])
+                s += float(lsm[r, t - 1, tk])
+                if tk == cfg.eos:
+                    break
+            out.append(s)
+        return torch.tensor(out)
+
+    assert (oracle_score(tokens) - score.cpu()).abs().max().item() < 3e-2
+    assert (score.cpu() >= oracle_score(g_tok) - 3e-2).all()
 
 
 @pytest.mark.parametrize("batch", [1, 3, 4, 9])
