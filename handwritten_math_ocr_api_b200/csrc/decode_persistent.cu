@@ -13,14 +13,17 @@
 // Math.  Projections run as  C^T[16 features x 8 rows] = W[16 x K] . X^T  with mma.sync.m16n8k16
 // (fp16 in, fp32 accumulate): the WEIGHTS are the M=16 operand and the cluster's 8 rows are exactly
 // the N=8 operand, so no tensor-core lane is wasted and one weight fragment is read from shared
-// memory exactly once.  tcgen05 needs M >= 64 rows and the step does 13-15 MFLOP per token: this
-// kernel is latency/bandwidth bound, not tensor bound.
+// memory exactly once.  The step does 13-15 MFLOP per token: this kernel is latency / L2-ingest bound,
+// not tensor bound (DESIGN.md 4.4 discusses tcgen05 for the fc_out phase).
 //
-// Weights.  Pre-packed per CTA as a stream of 8448-byte chunks (one m-tile: 16 features x 256 inputs,
-// see decode_persistent.cuh).  Chunk i of the stream belongs to warp (i mod 8): every warp owns ONE
-// shared-memory slot, waits for its chunk on its own mbarrier, runs its 16 mma, and immediately
-// re-arms the slot with its next chunk (cp.async.bulk, 8 chunks ahead in the stream).  Producer and
-// consumer of a slot are the same warp, so the ring needs no empty-barriers and no block barrier.
+// Weights.  Pre-packed per (CTA, warp) as a stream of "pieces" (decode_persistent.cuh): 16 features x a K-slice
+// of 64 or 128 input columns - what one warp consumes in one projection phase.  ALL 8 warps work in every
+// projection phase: the thin projections (32 or 64 features per CTA) are split along K, the partial tiles are
+// summed through shared memory (out_proj 8 warps x K/4, linear1 8 x K/2, linear2 8 x K/4); in_proj and fc_out
+// tiles stay on one warp, which accumulates their two K = 128 pieces in registers.  Every warp owns a ring of
+// two 4352-byte slots, waits for a piece on the slot's mbarrier, runs its 4-8 mma and immediately re-arms the slot
+// with the piece after next (cp.async.bulk).  Producer and consumer of a slot are the same warp, so the ring needs
+// no empty-barriers and no block barrier (only the cross-proxy fence of slot_release()).
 //
 // Exchange.  The activations of the 8 rows are all-gathered between the 8 CTAs through distributed
 // shared memory with st.async (remote store + complete_tx on an mbarrier of the DESTINATION CTA):
@@ -29,15 +32,14 @@
 // (arg-max partials).  barrier.cluster is used only at kernel start and end.
 //
 // Attention.  One warp per (row, head), on tensor cores: S = K q as mma.m16n8k16 with 16 cached keys
-// as the M operand (fp16 K cache [key][32], fragments loaded straight from global memory, 64 B per
-// key), softmax in fp32, then O = V^T p with 16 head dims as the M operand (fp16 V cache stored
-// TRANSPOSED, [dim][key], so its fragments are also plain 16-byte global loads); probabilities pass
-// through a 512-byte per-warp shared buffer.  ~45 instructions per 32 keys instead of ~200 on CUDA
-// cores; two 32-key blocks of K and of V are in flight per warp.  The caches are fp16 (not fp16): same
-// bytes, 3 more mantissa bits.  The cache rows of the NEXT layer are pulled into L2
-// (cp.async.bulk.prefetch.L2) one layer ahead.
+// as the M operand, softmax in fp32 on ex2, then O = V^T p with 16 head dims as the M operand.  Both caches are
+// fp16 and stored in the REGISTER ORDER of the mma A operand (fragment-major blocks of 32 keys x 32 dims = 2 KB),
+// so a fragment is one coalesced 16-byte load per lane; probabilities pass through an 80-word per-warp shared
+// buffer.  One 2 KB block of K (then V) is in flight per warp; a last block with <= 16 keys is read as 1 KB.
+// The cache rows of the NEXT layer are pulled into L2 (cp.async.bulk.prefetch.L2) one layer ahead; history
+// loads carry L2 evict_first, the weight stream and the memory K/V evict_last (they are re-read every step).
 //
-// Occupancy is part of the design: 106 KB of shared memory and <= 128 registers, so TWO CTAs (of
+// Occupancy is part of the design: ~104 KB of shared memory (greedy, T <= 160) and <= 128 registers, so TWO CTAs (of
 // different clusters) share an SM; B=256 runs as 32 clusters in a single wave.
 #include <cuda_fp16.h>
 
@@ -58,35 +60,40 @@ struct __align__(16) TopList { float v[DP_MAX_BEAM]; int i[DP_MAX_BEAM]; int pad
 struct Cand { float score; int flat; };
 struct Sel { float score; int parent; int tok; };
 
-struct Smem {
-  alignas(128) uint8_t slot[NW][DP_CHUNK];  // warp-private weight slots
+constexpr int NS = 2;                               // weight-piece slots per warp (ring)
+constexpr int STG_TILES = 8;                        // one partial tile per warp
+// BEAM = false drops the beam-search buffers; NB (32-key blocks per sequence) sizes the probability buffer.
+template <int NB, bool BEAM>
+struct SmemT {
+  alignas(128) uint8_t slot[NW][NS][DP_PIECE];  // warp-private weight slots
   alignas(16) float y32[R][D];              // pre-LayerNorm rows gathered from the 8 feature slices
   alignas(16) __half xa[R][PD];             // LayerNorm output (full rows), fp16 operand
   alignas(16) __half ctx[R][PD];            // attention context gathered from the 8 heads
   alignas(16) __half hf[R][PF];             // relu(linear1) gathered from the 8 slices
-  alignas(16) float stg[4][16][9];          // staging of GEMM tiles [task][feature][row] (hidden: fp16 [8][72])
+  alignas(16) float stg[STG_TILES][16][9];  // partial GEMM tiles of the K-split phases [warp][feature][row]
   alignas(16) float x32s[R][32];            // fp32 residual stream, this CTA's 32-feature slice only
   alignas(16) __half qh[R][HD];             // this head's scaled query (fp16 mma operand)
-  alignas(16) uint32_t pbuf[NW][128];       // per-warp softmax probabilities in P-operand order (half2 words)
+  alignas(16) uint32_t pbuf[NW][NB * 16];   // per-warp softmax probabilities in P-operand order (half2 words)
   alignas(16) __half knew[R][HD];           // this step's key / value of head c (appended to the caches after use)
   alignas(16) __half vnew[R][HD];
   Partial part[CL][R];                      // per-CTA argmax / sum-exp partials (gathered)
   Partial wpart[NW][R];                     // per-warp partials
   // beam search only
-  TopList wtop[NW][R];                      // per-warp top-K logits of every row
-  TopList ctop[CL][R];                      // per-CTA top-K, gathered from the 8 CTAs
-  Cand cand[R][DP_MAX_BEAM];                // candidate (score, hypothesis * V + token) of every row
+  TopList wtop[BEAM ? NW : 1][BEAM ? R : 1];   // per-warp top-K logits of every row
+  TopList ctop[BEAM ? CL : 1][BEAM ? R : 1];   // per-CTA top-K, gathered from the 8 CTAs
+  Cand cand[BEAM ? R : 1][DP_MAX_BEAM];     // candidate (score, hypothesis * V + token) of every row
   Sel sel[R];                               // chosen (score, parent row, token) of every new hypothesis
   float bscore[R];
   int bfin[R], bsrc[R];
-  alignas(8) uint64_t full[NW];
+  alignas(8) uint64_t full[NW][NS];
   alignas(8) uint64_t xbar[5];              // exchange barriers: context, y, hidden, partials, top-K lists
 };
 enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3, X_TOP = 4 };
 constexpr uint32_t XB_CTX = R * D * 2, XB_Y = R * D * 4, XB_HF = R * FF * 2, XB_PART = CL * R * sizeof(Partial);
 constexpr uint32_t XB_TOP = CL * R * sizeof(TopList);
-static_assert(sizeof(Smem) <= 112 * 1024, "two CTAs must fit one SM");
-static_assert(sizeof(float) * 4 * 16 * 9 >= sizeof(__half) * R * 72, "hidden staging aliases stg");
+// two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA.  (The T > 160 beam instantiation may take the SM alone.)
+static_assert(sizeof(SmemT<5, false>) <= 113 * 1024 && sizeof(SmemT<5, true>) <= 113 * 1024 &&
+              sizeof(SmemT<8, false>) <= 113 * 1024, "two CTAs must fit one SM");
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -142,15 +149,34 @@ __device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+// L2 residency (126 MB, two partitions).  Per decode step at B = 256 the kernel touches three kinds of bytes:
+//   * the weight stream (13.5 MB, read by EVERY cluster every step) and the memory K/V of cross-attention (67 MB,
+//     read by its cluster every step): reusable -> evict_last, they should stay L2-resident across steps;
+//   * the self-attention history (2 MB x t, every byte read exactly once per step, 315 MB at t = 150): streaming ->
+//     evict_first, so it does not push the reusable set out.
+// Policy operands are the fixed encodings of createpolicy.fractional.L2::evict_{first,last} with fraction 1.0.
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {     // weights: keep in L2
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                    smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(L2_EVICT_LAST)
                : "memory");
 }
+template <bool KEEP>
 __device__ __forceinline__ void prefetch_l2(const void* src, int bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes)
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes),
+               "l"(KEEP ? L2_EVICT_LAST : L2_EVICT_FIRST)
                : "memory");
+}
+// 16-byte cache-block load that bypasses L1 (every line is used once per SM) with an L2 eviction priority
+template <bool KEEP>
+__device__ __forceinline__ uint4 ld_kv(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(KEEP ? L2_EVICT_LAST : L2_EVICT_FIRST)
+               : "memory");
+  return v;
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -168,28 +194,25 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
 __device__ __forceinline__ __half to_half_sat(float x) { return to_h16(x); }                 // saturating (common.cuh)
 __device__ __forceinline__ uint32_t pack_half(float a, float b) { return pack16(a, b); }
 
-// C^T[16 features x 8 rows] = W[16 x 256] (one weight chunk, pitch PD) . X[8 rows x 256]^T (smem, pitch PB)
-//   c[0]: (feature lane/4, row 2*(lane%4)), c[1]: (same feature, row + 1), c[2], c[3]: feature + 8
-// Four independent accumulator chains keep the tensor pipe busy from a single warp.
-template <int PB>
-__device__ __forceinline__ void gemm16(const uint8_t* W, const __half* X, int lane, float (&c)[4]) {
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  const uint32_t a_addr = smem_u32(W) + ((lane & 15) * PD + (lane >> 4) * 8) * 2;
+// acc += C^T[16 features x 8 rows] = W[16 x 32*KIT] (one weight piece, pitch PW halves) . X[8 rows x 32*KIT]^T (shared
+// memory, pitch PB halves, already offset to the piece's first input column).  acc[0] / acc[1] are two independent
+// chains (even / odd 16-column k-steps); the caller adds them.
+//   acc[.][0]: (feature lane/4, row 2*(lane%4)), [1]: (same feature, row + 1), [2], [3]: feature + 8
+template <int KIT, int PW, int PB>
+__device__ __forceinline__ void gemm_piece(const uint8_t* W, const __half* X, int lane, float (&acc)[2][4]) {
+  const uint32_t a_addr = smem_u32(W) + ((lane & 15) * PW + (lane >> 4) * 8) * 2;
   const uint32_t b_addr = smem_u32(X) + ((lane & 7) * PB + (lane >> 3) * 8) * 2;
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk) {         // 32 input columns per iteration
+  for (int kk = 0; kk < KIT; ++kk) {         // 32 input columns per iteration
     uint32_t b[4], a0[4], a1[4];
     ldsm_x4(b_addr + kk * 64, b);
     ldsm_x4(a_addr + kk * 64, a0);
     ldsm_x4(a_addr + kk * 64 + 32, a1);
-    mma_f16(acc[(2 * kk) & 3], a0[0], a0[1], a0[2], a0[3], b[0], b[1]);
-    mma_f16(acc[(2 * kk + 1) & 3], a1[0], a1[1], a1[2], a1[3], b[2], b[3]);
+    mma_f16(acc[0], a0[0], a0[1], a0[2], a0[3], b[0], b[1]);
+    mma_f16(acc[1], a1[0], a1[1], a1[2], a1[3], b[2], b[3]);
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) c[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
 }
+constexpr int PW128 = 136, PW64 = 72;               // row pitches of the K = 128 / K = 64 pieces (halves)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -238,17 +261,31 @@ __device__ __forceinline__ int vfrag_half(int key_in_blk, int d) {      // half 
 template <int KV_SLOTS>
 struct KvSlots { uint4 r[KV_SLOTS][4]; };
 
-__device__ __forceinline__ void load_block(const uint4* base, int b, uint4 (&d)[4]) {
+// Block b of a (layer, row, head) region holding `n` keys in all.  In both layouts the first 1 KB of a block is its
+// first 16 keys (K: tile 0, V: k-step 0), so a last block with <= 16 keys is read as 1 KB, not 2 (the other half is
+// the unwritten tail: its scores are masked and its probabilities are zero - the registers are zeroed so that 0 x V
+// stays finite).  MEM: memory K/V of cross-attention (re-read every step -> evict_last); history -> evict_first.
+template <bool MEM>
+__device__ __forceinline__ void load_block(const uint4* base, int b, int n, uint4 (&d)[4]) {
+  const bool half = n - 32 * b <= 16;                                // warp-uniform
 #pragma unroll
-  for (int u = 0; u < 4; ++u) d[u] = __ldcg(base + 128 * b + 32 * u);
+  for (int u = 0; u < 2; ++u) d[u] = ld_kv<MEM>(base + 128 * b + 32 * u);
+  if (half) {
+    d[2] = make_uint4(0u, 0u, 0u, 0u); d[3] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+#pragma unroll
+    for (int u = 2; u < 4; ++u) d[u] = ld_kv<MEM>(base + 128 * b + 32 * u);
+  }
 }
-template <int NB, int KV_SLOTS>
+// bytes of a region that hold its first `keys` keys at 1 KB granularity (for the L2 prefetch)
+__device__ __forceinline__ int region_bytes(int keys) { return ((keys + 15) >> 4) * 1024; }
+template <int NB, int KV_SLOTS, bool MEM>
 __device__ __forceinline__ void attend_issue(const __half* Kc, int n, int lane, KvSlots<KV_SLOTS>& kv) {
   const int nb = (n + 31) >> 5;
   const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;       // + 128 * block + 32 * fragment
 #pragma unroll
   for (int b = 0; b < KV_SLOTS && b < NB; ++b)
-    if (b < nb) load_block(Kl, b, kv.r[b]);
+    if (b < nb) load_block<MEM>(Kl, b, n, kv.r[b]);
 }
 // If COPY (beam search), every consumed history block is also stored to (Kd, Vd): the destination row of the
 // other cache set - the parent gather of the beam reorder rides on the attention loads.
@@ -256,7 +293,7 @@ __device__ __forceinline__ void store_block(uint4* base, int b, const uint4 (&d)
 #pragma unroll
   for (int u = 0; u < 4; ++u) __stcg(base + 128 * b + 32 * u, d[u]);
 }
-template <int NB, bool NEW, bool COPY, int KV_SLOTS>
+template <int NB, bool NEW, bool COPY, int KV_SLOTS, bool MEM>
 __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, const __half* Vc, int n,
                                            const __half* knew, const __half* vnew, uint32_t* pbuf, int lane,
                                            KvSlots<KV_SLOTS>& kv, float (&out)[4], long long* tr, __half* Kd = nullptr,
@@ -296,8 +333,8 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
         sc[4 * b + 2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
       }
       if (COPY && Kd != nullptr) store_block(reinterpret_cast<uint4*>(Kd) + lane, b, d);
-      if (b + KV_SLOTS < NB && b + KV_SLOTS < nb) load_block(Kl, b + KV_SLOTS, d);       // next K block of this slot ...
-      else load_block(Vl, b % KV_SLOTS, d);                                // ... or its first V block (b & 3 < nb here)
+      if (b + KV_SLOTS < NB && b + KV_SLOTS < nb) load_block<MEM>(Kl, b + KV_SLOTS, n, d);       // next K block of this slot ...
+      else load_block<MEM>(Vl, b % KV_SLOTS, n, d);                                // ... or its first V block (b & 3 < nb here)
     } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) sc[4 * b + u] = -INFINITY;
@@ -337,7 +374,7 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
       mma_f16(acc0, d[2].x, d[2].y, d[2].z, d[2].w, p1.x, p1.y);
       mma_f16(acc1, d[3].x, d[3].y, d[3].z, d[3].w, p1.x, p1.y);
       if (COPY && Vd != nullptr) store_block(reinterpret_cast<uint4*>(Vd) + lane, b, d);
-      if (b + KV_SLOTS < NB && b + KV_SLOTS < nb) load_block(Vl, b + KV_SLOTS, d);
+      if (b + KV_SLOTS < NB && b + KV_SLOTS < nb) load_block<MEM>(Vl, b + KV_SLOTS, n, d);
     }
   }
 #pragma unroll
@@ -426,10 +463,12 @@ struct TopK<0> {                                                  // greedy inst
   __device__ __forceinline__ void insert(float, int) {}
 };
 
-// The fp32 bias of weight row r travels in the padding of that row (halves 256, 257 of 264): it arrives with
-// the weights, costs no extra copy, barrier or shared memory, and is read before the slot is released.
-__device__ __forceinline__ float chunk_bias(const uint8_t* slot, int r) {
-  return *reinterpret_cast<const float*>(slot + (r * PD + D) * 2);
+// The fp32 bias of weight row r travels in the padding of that row (the two halves after its NC columns) of the piece
+// that holds the row's first K-slice (zero in the others): it arrives with the weights, costs no extra copy, barrier
+// or shared memory, and is read before the slot is released.
+template <int NC>
+__device__ __forceinline__ float piece_bias(const uint8_t* slot, int r) {
+  return *reinterpret_cast<const float*>(slot + (r * (NC + 8) + NC) * 2);
 }
 
 // KB = 0: greedy.  KB = DP_MAX_BEAM: beam search with p.beam <= KB hypotheses per image (see decode_persistent.cuh).
@@ -642,7 +681,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       __half* Vd = p.vcache + set_wr + (size_t)l * kv_layer + kv_row;
       TR();
       // ---- self-attention: q, k, v of head c = 6 tiles ---------------------------------------------
-      if (lane < 2 && !(dev_flags & 2)) prefetch_l2((lane ? p.memv : p.memk) + (size_t)l * m_layer + m_row, 2048);   // this layer's memory K/V -> L2
+      if (lane < 2 && !(dev_flags & 2)) prefetch_l2<true>((lane ? p.memv : p.memk) + (size_t)l * m_layer + m_row, region_bytes(p.mem_len));   // this layer's memory K/V -> L2
       {
         const int j = (warp - g) & 7;
         if (j < 6) {
@@ -667,14 +706,14 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       KvSlots<KVS> kv;
       const int nhist = (dev_flags & 8) ? min(t, 1) : t;
-      attend_issue<NB, KVS>(Kc, nhist, lane, kv);       // history K blocks fly across the barrier
+      attend_issue<NB, KVS, false>(Kc, nhist, lane, kv);       // history K blocks fly across the barrier
       TR();
       __syncthreads();
       TR();
       {
         float o[4];
         long long* tr = (tracing && t == p.trace_step && ti + 3 < 1024) ? p.trace + ti : nullptr;
-        attend_mma<NB, true, BEAM, KVS>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0],
+        attend_mma<NB, true, BEAM, KVS, false>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0],
                                    lane, kv, o, tr, row_ok ? Kd : nullptr, row_ok ? Vd : nullptr);   // padding warps
         // recompute the last valid row: they must not copy its blocks (a late copy would overwrite the append below)
         if (tr) ti += 3;
@@ -690,7 +729,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         const int keys = last ? t + 1 : t;
         if (!BEAM && keys > 0 && lane < 2 && !(dev_flags & 1)) {
           const size_t nxt = last ? set_wr + kv_row : set_rd + (size_t)(l + 1) * kv_layer + kv_src;
-          prefetch_l2((lane ? p.vcache : p.kcache) + nxt, ((keys + 31) >> 5) * 2048);
+          prefetch_l2<false>((lane ? p.vcache : p.kcache) + nxt, region_bytes(keys));
         }
       }
       TR();
@@ -735,12 +774,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       const __half* Mk = p.memk + (size_t)l * m_layer + m_row;       // (not live across the self-attention block)
       const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
-      attend_issue<1, KVS>(Mk, p.mem_len, lane, kv);
+      attend_issue<1, KVS, true>(Mk, p.mem_len, lane, kv);
       __syncthreads();
       TR();
       {
         float o[4];
-        attend_mma<1, false, false, KVS>(&s.qh[warp][0], Mk, Mv, p.mem_len, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
+        attend_mma<1, false, false, KVS, true>(&s.qh[warp][0], Mk, Mv, p.mem_len, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
         send_ctx(o);
       }
       TR();

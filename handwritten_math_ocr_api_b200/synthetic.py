@@ -90,14 +90,28 @@ def _scale_for(name: str, shape, cfg: ModelConfig, fc_gain: float) -> tuple:
     return gain * s3 / math.sqrt(fan_in), 0.0
 
 
+def next_token_permutation(vocab_size: int) -> np.ndarray:
+    """The fixed map prev-token -> favoured next token of the ``peak`` checkpoints: 4 + (2 v + 7) mod (V - 4)
+    (a permutation of the non-special ids when V - 4 is odd, as for V = 5075)."""
+    return 4 + (np.arange(vocab_size, dtype=np.int64) * 2 + 7) % (vocab_size - 4)
+
+
 def synth_state_dict(cfg: ModelConfig | None = None, seed: int = 0, fc_gain: float = 4.0,
-                     eos_bias_sigma: float = 2.5) -> Dict[str, torch.Tensor]:
+                     eos_bias_sigma: float = 2.5, peak: float = 0.0) -> Dict[str, torch.Tensor]:
     """Reference-layout state dict (517 entries, ``encoder.features.*`` aliasing
     ``encoder.swin.features.*``) filled with the deterministic synthetic values.
 
     ``eos_bias_sigma`` lifts ``fc_out.bias[eos]`` by that many logit standard deviations so
     greedy decodes terminate at varied lengths (0 => essentially never emits EOS, the fixed
-    150-step benchmark workload of SURVEY.md section 8d)."""
+    150-step benchmark workload of SURVEY.md section 8d).
+
+    ``peak`` > 0 gives the logits the PEAKED shape a trained model has.  Scaling ``fc_out``
+    (``fc_gain``) cannot do that: it scales the margins and the arithmetic error alike, so the rate of near-tie argmax
+    flips does not change (measured: 96.2 / 96.6 / 96.6 % identical sequences at fc_gain 4 / 16 / 32).  Instead a
+    readout of the previous token is added: ``fc_out.weight[next(v)] += peak * embedding[v] / |embedding[v]|``.  The
+    final hidden state still carries the fed token's embedding (the decoder's sub-layer outputs are small), so the
+    favoured token's logit rises by about ``0.7 * peak * |e|``; at peak 8 the oracle's top-1 probability has median
+    0.97 (random init: 0.30) while the image still decides the uncertain steps."""
     cfg = cfg or ModelConfig()
     sd: Dict[str, torch.Tensor] = {}
     for name, shape, dtype in state_dict_layout(cfg):
@@ -117,6 +131,12 @@ def synth_state_dict(cfg: ModelConfig | None = None, seed: int = 0, fc_gain: flo
         sd[name] = torch.from_numpy(vals)
     if eos_bias_sigma:
         sd["decoder.fc_out.bias"][cfg.eos] += float(eos_bias_sigma) * fc_gain
+    if peak:
+        emb = sd["decoder.embedding.weight"].numpy().astype(np.float64)
+        unit = emb / np.sqrt((emb * emb).sum(1, keepdims=True))
+        w = sd["decoder.fc_out.weight"].numpy().astype(np.float64)
+        np.add.at(w, next_token_permutation(cfg.vocab_size), float(peak) * unit)
+        sd["decoder.fc_out.weight"] = torch.from_numpy(w.astype(np.float32))
     return sd
 
 
