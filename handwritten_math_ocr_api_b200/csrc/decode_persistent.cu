@@ -13,17 +13,14 @@
 // Math.  Projections run as  C^T[16 features x 8 rows] = W[16 x K] . X^T  with mma.sync.m16n8k16
 // (fp16 in, fp32 accumulate): the WEIGHTS are the M=16 operand and the cluster's 8 rows are exactly
 // the N=8 operand, so no tensor-core lane is wasted and one weight fragment is read from shared
-// memory exactly once.  The step does 13-15 MFLOP per token: this kernel is latency / L2-ingest bound,
-// not tensor bound (DESIGN.md 4.4 discusses tcgen05 for the fc_out phase).
+// memory exactly once.  tcgen05 needs M >= 64 rows and the step does 13-15 MFLOP per token: this
+// kernel is latency/bandwidth bound, not tensor bound.
 //
-// Weights.  Pre-packed per (CTA, warp) as a stream of "pieces" (decode_persistent.cuh): 16 features x a K-slice
-// of 64 or 128 input columns - what one warp consumes in one projection phase.  ALL 8 warps work in every
-// projection phase: the thin projections (32 or 64 features per CTA) are split along K, the partial tiles are
-// summed through shared memory (out_proj 8 warps x K/4, linear1 8 x K/2, linear2 8 x K/4); in_proj and fc_out
-// tiles stay on one warp, which accumulates their two K = 128 pieces in registers.  Every warp owns a ring of
-// two 4352-byte slots, waits for a piece on the slot's mbarrier, runs its 4-8 mma and immediately re-arms the slot
-// with the piece after next (cp.async.bulk).  Producer and consumer of a slot are the same warp, so the ring needs
-// no empty-barriers and no block barrier (only the cross-proxy fence of slot_release()).
+// Weights.  Pre-packed per CTA as a stream of 8448-byte chunks (one m-tile: 16 features x 256 inputs,
+// see decode_persistent.cuh).  Chunk i of the stream belongs to warp (i mod 8): every warp owns ONE
+// shared-memory slot, waits for its chunk on its own mbarrier, runs its 16 mma, and immediately
+// re-arms the slot with its next chunk (cp.async.bulk, 8 chunks ahead in the stream).  Producer and
+// consumer of a slot are the same warp, so the ring needs no empty-barriers and no block barrier.
 //
 // Exchange.  The activations of the 8 rows are all-gathered between the 8 CTAs through distributed
 // shared memory with st.async (remote store + complete_tx on an mbarrier of the DESTINATION CTA):
@@ -60,40 +57,35 @@ struct __align__(16) TopList { float v[DP_MAX_BEAM]; int i[DP_MAX_BEAM]; int pad
 struct Cand { float score; int flat; };
 struct Sel { float score; int parent; int tok; };
 
-constexpr int NS = 2;                               // weight-piece slots per warp (ring)
-constexpr int STG_TILES = 8;                        // one partial tile per warp
-// BEAM = false drops the beam-search buffers; NB (32-key blocks per sequence) sizes the probability buffer.
-template <int NB, bool BEAM>
-struct SmemT {
-  alignas(128) uint8_t slot[NW][NS][DP_PIECE];  // warp-private weight slots
+struct Smem {
+  alignas(128) uint8_t slot[NW][DP_CHUNK];  // warp-private weight slots
   alignas(16) float y32[R][D];              // pre-LayerNorm rows gathered from the 8 feature slices
   alignas(16) __half xa[R][PD];             // LayerNorm output (full rows), fp16 operand
   alignas(16) __half ctx[R][PD];            // attention context gathered from the 8 heads
   alignas(16) __half hf[R][PF];             // relu(linear1) gathered from the 8 slices
-  alignas(16) float stg[STG_TILES][16][9];  // partial GEMM tiles of the K-split phases [warp][feature][row]
+  alignas(16) float stg[4][16][9];          // staging of GEMM tiles [task][feature][row] (hidden: fp16 [8][72])
   alignas(16) float x32s[R][32];            // fp32 residual stream, this CTA's 32-feature slice only
   alignas(16) __half qh[R][HD];             // this head's scaled query (fp16 mma operand)
-  alignas(16) uint32_t pbuf[NW][NB * 16];   // per-warp softmax probabilities in P-operand order (half2 words)
+  alignas(16) uint32_t pbuf[NW][128];       // per-warp softmax probabilities in P-operand order (half2 words)
   alignas(16) __half knew[R][HD];           // this step's key / value of head c (appended to the caches after use)
   alignas(16) __half vnew[R][HD];
   Partial part[CL][R];                      // per-CTA argmax / sum-exp partials (gathered)
   Partial wpart[NW][R];                     // per-warp partials
   // beam search only
-  TopList wtop[BEAM ? NW : 1][BEAM ? R : 1];   // per-warp top-K logits of every row
-  TopList ctop[BEAM ? CL : 1][BEAM ? R : 1];   // per-CTA top-K, gathered from the 8 CTAs
-  Cand cand[BEAM ? R : 1][DP_MAX_BEAM];     // candidate (score, hypothesis * V + token) of every row
+  TopList wtop[NW][R];                      // per-warp top-K logits of every row
+  TopList ctop[CL][R];                      // per-CTA top-K, gathered from the 8 CTAs
+  Cand cand[R][DP_MAX_BEAM];                // candidate (score, hypothesis * V + token) of every row
   Sel sel[R];                               // chosen (score, parent row, token) of every new hypothesis
   float bscore[R];
   int bfin[R], bsrc[R];
-  alignas(8) uint64_t full[NW][NS];
+  alignas(8) uint64_t full[NW];
   alignas(8) uint64_t xbar[5];              // exchange barriers: context, y, hidden, partials, top-K lists
 };
 enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3, X_TOP = 4 };
 constexpr uint32_t XB_CTX = R * D * 2, XB_Y = R * D * 4, XB_HF = R * FF * 2, XB_PART = CL * R * sizeof(Partial);
 constexpr uint32_t XB_TOP = CL * R * sizeof(TopList);
-// two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA.  (The T > 160 beam instantiation may take the SM alone.)
-static_assert(sizeof(SmemT<5, false>) <= 113 * 1024 && sizeof(SmemT<5, true>) <= 113 * 1024 &&
-              sizeof(SmemT<8, false>) <= 113 * 1024, "two CTAs must fit one SM");
+static_assert(sizeof(Smem) <= 112 * 1024, "two CTAs must fit one SM");
+static_assert(sizeof(float) * 4 * 16 * 9 >= sizeof(__half) * R * 72, "hidden staging aliases stg");
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -194,25 +186,28 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
 __device__ __forceinline__ __half to_half_sat(float x) { return to_h16(x); }                 // saturating (common.cuh)
 __device__ __forceinline__ uint32_t pack_half(float a, float b) { return pack16(a, b); }
 
-// acc += C^T[16 features x 8 rows] = W[16 x 32*KIT] (one weight piece, pitch PW halves) . X[8 rows x 32*KIT]^T (shared
-// memory, pitch PB halves, already offset to the piece's first input column).  acc[0] / acc[1] are two independent
-// chains (even / odd 16-column k-steps); the caller adds them.
-//   acc[.][0]: (feature lane/4, row 2*(lane%4)), [1]: (same feature, row + 1), [2], [3]: feature + 8
-template <int KIT, int PW, int PB>
-__device__ __forceinline__ void gemm_piece(const uint8_t* W, const __half* X, int lane, float (&acc)[2][4]) {
-  const uint32_t a_addr = smem_u32(W) + ((lane & 15) * PW + (lane >> 4) * 8) * 2;
+// C^T[16 features x 8 rows] = W[16 x 256] (one weight chunk, pitch PD) . X[8 rows x 256]^T (smem, pitch PB)
+//   c[0]: (feature lane/4, row 2*(lane%4)), c[1]: (same feature, row + 1), c[2], c[3]: feature + 8
+// Four independent accumulator chains keep the tensor pipe busy from a single warp.
+template <int PB>
+__device__ __forceinline__ void gemm16(const uint8_t* W, const __half* X, int lane, float (&c)[4]) {
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const uint32_t a_addr = smem_u32(W) + ((lane & 15) * PD + (lane >> 4) * 8) * 2;
   const uint32_t b_addr = smem_u32(X) + ((lane & 7) * PB + (lane >> 3) * 8) * 2;
 #pragma unroll
-  for (int kk = 0; kk < KIT; ++kk) {         // 32 input columns per iteration
+  for (int kk = 0; kk < 8; ++kk) {         // 32 input columns per iteration
     uint32_t b[4], a0[4], a1[4];
     ldsm_x4(b_addr + kk * 64, b);
     ldsm_x4(a_addr + kk * 64, a0);
     ldsm_x4(a_addr + kk * 64 + 32, a1);
-    mma_f16(acc[0], a0[0], a0[1], a0[2], a0[3], b[0], b[1]);
-    mma_f16(acc[1], a1[0], a1[1], a1[2], a1[3], b[2], b[3]);
+    mma_f16(acc[(2 * kk) & 3], a0[0], a0[1], a0[2], a0[3], b[0], b[1]);
+    mma_f16(acc[(2 * kk + 1) & 3], a1[0], a1[1], a1[2], a1[3], b[2], b[3]);
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
 }
-constexpr int PW128 = 136, PW64 = 72;               // row pitches of the K = 128 / K = 64 pieces (halves)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -463,12 +458,10 @@ struct TopK<0> {                                                  // greedy inst
   __device__ __forceinline__ void insert(float, int) {}
 };
 
-// The fp32 bias of weight row r travels in the padding of that row (the two halves after its NC columns) of the piece
-// that holds the row's first K-slice (zero in the others): it arrives with the weights, costs no extra copy, barrier
-// or shared memory, and is read before the slot is released.
-template <int NC>
-__device__ __forceinline__ float piece_bias(const uint8_t* slot, int r) {
-  return *reinterpret_cast<const float*>(slot + (r * (NC + 8) + NC) * 2);
+// The fp32 bias of weight row r travels in the padding of that row (halves 256, 257 of 264): it arrives with
+// the weights, costs no extra copy, barrier or shared memory, and is read before the slot is released.
+__device__ __forceinline__ float chunk_bias(const uint8_t* slot, int r) {
+  return *reinterpret_cast<const float*>(slot + (r * PD + D) * 2);
 }
 
 // KB = 0: greedy.  KB = DP_MAX_BEAM: beam search with p.beam <= KB hypotheses per image (see decode_persistent.cuh).

@@ -6,37 +6,30 @@
 
 namespace hmocr {
 
-// Packed weight stream (fp16, values saturated to +-65504).  Every warp of every CTA has its OWN stream of "pieces":
-// a piece = 16 weight rows (output features, one mma m-tile) x a K-slice of the input columns, rows padded by 8 halves so
-// ldmatrix is bank-conflict free, and it is exactly what ONE warp consumes in ONE projection phase.  The fp32 bias of a
-// row travels in that padding (the first two pad halves) of the piece that holds the row's FIRST K-slice; the other
-// slices carry zero.  Every piece is one cp.async.bulk copy; pieces sit at a fixed stride of DP_PIECE bytes.
+// Packed weight stream (fp16: same bytes as fp16, 3 more mantissa bits; values are saturated to +-65504).  One chunk = one mma m-tile of a projection: 16 weight rows (output
+// features) x 256 input columns, rows padded to 264 elements so ldmatrix is bank-conflict free.
+// Every chunk is one cp.async.bulk copy of DP_CHUNK bytes.
 //
-// wstream[cta c][warp w][piece]: per layer, in consumption order
-//    warps 0..5:  in_proj rows of head c - tile j = w: part = j / 2 (q, k, v), rows [c*32 + 16 (j % 2) ..]:
-//                 two K = 128 pieces (columns 0..127, 128..255) accumulated by the same warp
-//    all warps:   self_attn.out_proj   rows [c*32 + 16 (w / 4) ..], columns [64 (w % 4) ..]      K = 64 piece
-//                 multihead_attn q     rows [c*32 + 16 (w / 4) ..], columns [64 (w % 4) ..]      K = 64 piece
-//                 multihead_attn.out_proj                      (same split)                     K = 64 piece
-//                 linear1              rows [c*64 + 16 (w / 2) ..], columns [128 (w % 2) ..]     K = 128 piece
-//                 linear2              rows [c*32 + 16 (w / 4) ..], columns [128 (w % 4) ..]     K = 128 piece (of 512)
-// then per step fc_tiles / 8 tiles of fc_out: rows [c*16*fc_tiles + 16 (w + 8 i) ..], two K = 128 pieces each.
-// So ALL 8 warps work in every projection phase; the partial tiles of a K-split are summed through shared memory.
+// wstream[cta c][chunk]: per layer (DP_LAYER_CHUNKS chunks)
+//    0,1    self_attn.in_proj  q rows of head c          [c*32 + 16m ..]
+//    2,3    self_attn.in_proj  k rows of head c
+//    4,5    self_attn.in_proj  v rows of head c
+//    6,7    self_attn.out_proj rows                      [c*32 + 16m ..]
+//    8,9    multihead_attn.in_proj q rows of head c
+//   10,11   multihead_attn.out_proj rows                 [c*32 + 16m ..]
+//   12..15  linear1 rows                                 [c*64 + 16m ..]
+//   16..19  linear2 rows [c*32 + 16m ..], input columns [256*kh .. 256*kh+255]; order (m,kh) = 00,01,10,11
+// then fc_tiles chunks of fc_out: rows [c*16*fc_tiles + 16m ..] (zero rows past the vocabulary).
 constexpr int DP_CH_ROWS = 16;
-constexpr int DP_PIECE = DP_CH_ROWS * 136 * 2;     // 4352 B: 16 rows x 128 columns (+ 8 pad)
-constexpr int DP_PIECE_Q = DP_CH_ROWS * 72 * 2;    // 2304 B: 16 rows x 64 columns (+ 8 pad)
-constexpr int DP_QKV_WARPS = 6;                    // warps that own an in_proj tile
-// pieces per layer of a warp, and per step
-constexpr int dp_layer_pieces(int warp) { return warp < DP_QKV_WARPS ? 7 : 5; }
-constexpr int dp_step_pieces(int warp, int layers, int fc_tiles) { return dp_layer_pieces(warp) * layers + 2 * (fc_tiles / 8); }
-// bytes between the streams of two warps / two CTAs
-inline size_t dp_warp_stride(int layers, int fc_tiles) { return (size_t)dp_step_pieces(0, layers, fc_tiles) * DP_PIECE; }
-inline size_t dp_cta_stride(int layers, int fc_tiles) { return 8 * dp_warp_stride(layers, fc_tiles); }
+constexpr int DP_CHUNK = DP_CH_ROWS * 264 * 2;   // 8448 B
+constexpr int DP_LAYER_CHUNKS = 20;
 
+// The fp32 bias of every weight row travels in the padding of that row (halves 256, 257 of 264); the second
+// input-half chunks of linear2 carry zeros.
 constexpr int DP_ROWS = 8;          // sequences owned by one cluster (= the N of mma.m16n8k16)
 
 struct DecPersistParams {
-  const uint8_t* wstream;     // [8 CTAs][8 warps][pieces per step][DP_PIECE] (layout above)
+  const uint8_t* wstream;     // [8][chunks_per_step][DP_CHUNK]
   const float* lnparams;      // [L][6][256]: norm1.weight, norm1.bias, norm2.weight, ... norm3.bias
   const float* emb;           // [vocab][256]
   const float* pos;           // [max_pos][256]
@@ -66,7 +59,7 @@ struct DecPersistParams {
   int* bm_tok;                // [rows] token fed at the next step
   int* bp_parent;             // [max_len][rows] beam index (within the image) of the parent chosen at step t
   int* bp_token;              // [max_len][rows] token chosen at step t
-  int num_layers, fc_tiles, vocab;
+  int num_layers, fc_tiles, chunks_per_step, vocab;
   int tmax, max_pos, max_len, ld_tok, eos, pad;
   long long* trace;           // optional: clock64() of cluster 0 / CTA 0 / thread 0 at every phase boundary
   int trace_step;             //           of decode step `trace_step`
