@@ -389,6 +389,98 @@ __device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, c
   __syncwarp();                                                     // pbuf may be rewritten by the next call
 }
 
+// ---- one-pass (online-softmax) variant ------------------------------------------------------------------
+// The two-pass form above keeps ONE 2 KB block in flight per warp: every K block, then every V block, pays a full
+// L2 round trip behind the previous one, and the softmax between them overlaps nothing.  Here the K and the V block
+// of the same 32 keys travel TOGETHER (two register slots, 4 KB in flight per warp) and every block is finished
+// before the next: scores -> running maximum -> probabilities -> accumulators rescaled -> P.V.  The next K block
+// is requested as soon as the scores of this one exist, the next V block as soon as its P.V is issued, so the
+// softmax arithmetic of block b hides under the loads of block b+1, and the 4 * NB score registers of the
+// two-pass form are gone.  The P operand needs no shared memory: the V cache's key order makes the packed pair
+// {p[key g], p[key g+8]} of lane group g exactly the half2 that lanes t = g (b0) and t = g - 4 (b1) feed to the
+// mma, so two shuffles per 16 keys replace the store / __syncwarp / load round trip.
+struct KvPair { uint4 k[4], v[4]; };
+template <bool MEM>
+__device__ __forceinline__ void attend_issue2(const __half* Kc, const __half* Vc, int n, int lane, KvPair& kv) {
+  if (n > 0) {                                                       // warp-uniform
+    load_block<MEM>(reinterpret_cast<const uint4*>(Kc) + lane, 0, n, kv.k);
+    load_block<MEM>(reinterpret_cast<const uint4*>(Vc) + lane, 0, n, kv.v);
+  }
+}
+template <int NB, bool NEW, bool COPY, bool MEM>
+__device__ __forceinline__ void attend_online(const __half* qh, const __half* Kc, const __half* Vc, int n,
+                                              const __half* knew, const __half* vnew, int lane, KvPair& kv,
+                                              float (&out)[4], __half* Kd = nullptr, __half* Vd = nullptr) {
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const uint2 q0 = *reinterpret_cast<const uint2*>(qh + 4 * t4), q1 = *reinterpret_cast<const uint2*>(qh + 16 + 4 * t4);
+  const int nb = (n + 31) >> 5;
+  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;
+  const uint4* Vl = reinterpret_cast<const uint4*>(Vc) + lane;
+  float m = -INFINITY, den = 0.f;                                    // den: this lane's share (its two keys per tile)
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (NEW) {                                                         // this step's own key / value start the recurrence
+    const uint4 kn = *reinterpret_cast<const uint4*>(knew + t4 * 8), qn = *reinterpret_cast<const uint4*>(qh + t4 * 8);
+    const uint32_t qw[4] = {qn.x, qn.y, qn.z, qn.w}, kw[4] = {kn.x, kn.y, kn.z, kn.w};
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[i]));
+      const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&kw[i]));
+      a = fmaf(qf.x, kf.x, a); a = fmaf(qf.y, kf.y, a);
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    m = a;                                                           // p = 2^0 = 1 exactly
+    den = (g4 == 0) ? 1.f : 0.f;                                     // counted once in the reduction over g4
+    const uint2 vn = *reinterpret_cast<const uint2*>(vnew + 4 * g4);
+    const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&vn.x));
+    const float2 v23 = __half22float2(*reinterpret_cast<const __half2*>(&vn.y));
+    acc0[0] = v01.x; acc0[2] = v01.y; acc1[0] = v23.x; acc1[2] = v23.y;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (b < nb) {                                                    // warp-uniform
+      float sc[4];
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(c, kv.k[2 * tile].x, kv.k[2 * tile].y, kv.k[2 * tile].z, kv.k[2 * tile].w, q0.x, q0.y);
+        mma_f16(c, kv.k[2 * tile + 1].x, kv.k[2 * tile + 1].y, kv.k[2 * tile + 1].z, kv.k[2 * tile + 1].w, q1.x, q1.y);
+        const int key = 32 * b + 16 * tile + g4;
+        sc[2 * tile] = (key < n) ? c[0] : -INFINITY;
+        sc[2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
+      }
+      if (COPY && Kd != nullptr) store_block(reinterpret_cast<uint4*>(Kd) + lane, b, kv.k);
+      if (b + 1 < NB && b + 1 < nb) load_block<MEM>(Kl, b + 1, n, kv.k);
+      float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+      const float mn = fmaxf(m, bm);                                 // finite: the block holds at least one key
+      const float rs = ex2f(m - mn);                                 // 0 on the first block without NEW (m = -inf)
+      m = mn;
+      const __half2 ph0 = __floats2half2_rn(ex2f(sc[0] - m), ex2f(sc[1] - m));
+      const __half2 ph1 = __floats2half2_rn(ex2f(sc[2] - m), ex2f(sc[3] - m));
+      const float2 pf0 = __half22float2(ph0), pf1 = __half22float2(ph1);   // normalise with the rounded weights
+      den = fmaf(den, rs, (pf0.x + pf0.y) + (pf1.x + pf1.y));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc0[i] *= rs; acc1[i] *= rs; }
+      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&ph0), w1 = *reinterpret_cast<const uint32_t*>(&ph1);
+      const uint32_t p0x = __shfl_sync(0xffffffffu, w0, t4 << 2), p0y = __shfl_sync(0xffffffffu, w0, (t4 + 4) << 2);
+      const uint32_t p1x = __shfl_sync(0xffffffffu, w1, t4 << 2), p1y = __shfl_sync(0xffffffffu, w1, (t4 + 4) << 2);
+      mma_f16(acc0, kv.v[0].x, kv.v[0].y, kv.v[0].z, kv.v[0].w, p0x, p0y);
+      mma_f16(acc1, kv.v[1].x, kv.v[1].y, kv.v[1].z, kv.v[1].w, p0x, p0y);
+      mma_f16(acc0, kv.v[2].x, kv.v[2].y, kv.v[2].z, kv.v[2].w, p1x, p1y);
+      mma_f16(acc1, kv.v[3].x, kv.v[3].y, kv.v[3].z, kv.v[3].w, p1x, p1y);
+      if (COPY && Vd != nullptr) store_block(reinterpret_cast<uint4*>(Vd) + lane, b, kv.v);
+      if (b + 1 < NB && b + 1 < nb) load_block<MEM>(Vl, b + 1, n, kv.v);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const float inv = __fdividef(1.0f, den);
+  out[0] = acc0[0] * inv; out[1] = acc0[2] * inv; out[2] = acc1[0] * inv; out[3] = acc1[2] * inv;
+}
+
 __device__ __forceinline__ void merge_partial(Partial& a, const Partial& b) {
   // combine (max, first-argmax, sum exp(x - max)); ties -> lower index (torch.argmax)
   if (b.m > a.m || (b.m == a.m && b.idx < a.idx)) {
@@ -697,19 +789,18 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         }
         g += 6;
       }
-      KvSlots<KVS> kv;
+      KvPair kv;
       const int nhist = (dev_flags & 8) ? min(t, 1) : t;
-      attend_issue<NB, KVS, false>(Kc, nhist, lane, kv);       // history K blocks fly across the barrier
+      attend_issue2<false>(Kc, Vc, nhist, lane, kv);           // the first K and V block fly across the barrier
       TR();
       __syncthreads();
       TR();
       {
         float o[4];
-        long long* tr = (tracing && t == p.trace_step && ti + 3 < 1024) ? p.trace + ti : nullptr;
-        attend_mma<NB, true, BEAM, KVS, false>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0], &s.pbuf[warp][0],
-                                   lane, kv, o, tr, row_ok ? Kd : nullptr, row_ok ? Vd : nullptr);   // padding warps
+        attend_online<NB, true, BEAM, false>(&s.qh[warp][0], Kc, Vc, nhist, &s.knew[warp][0], &s.vnew[warp][0],
+                                             lane, kv, o, row_ok ? Kd : nullptr, row_ok ? Vd : nullptr);   // padding warps
         // recompute the last valid row: they must not copy its blocks (a late copy would overwrite the append below)
-        if (tr) ti += 3;
+        TR();
         send_ctx(o);
         if (BEAM) __syncwarp();                                // the block copies above are ordered before the append
         if (row_ok) {                                          // append this step's key / value (fragment-major)
@@ -767,12 +858,12 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       const __half* Mk = p.memk + (size_t)l * m_layer + m_row;       // (not live across the self-attention block)
       const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
-      attend_issue<1, KVS, true>(Mk, p.mem_len, lane, kv);
+      attend_issue2<true>(Mk, Mv, p.mem_len, lane, kv);
       __syncthreads();
       TR();
       {
         float o[4];
-        attend_mma<1, false, false, KVS, true>(&s.qh[warp][0], Mk, Mv, p.mem_len, nullptr, nullptr, &s.pbuf[warp][0], lane, kv, o, nullptr);
+        attend_online<1, false, false, true>(&s.qh[warp][0], Mk, Mv, p.mem_len, nullptr, nullptr, lane, kv, o);
         send_ctx(o);
       }
       TR();

@@ -15,7 +15,7 @@ from handwritten_math_ocr_api_b200 import FormulaRecognitionModel, _lib  # noqa:
 from handwritten_math_ocr_api_b200.layout import ModelConfig  # noqa: E402
 from handwritten_math_ocr_api_b200.synthetic import synth_images, synth_state_dict  # noqa: E402
 
-LAYER = ["qkv: wait for the weight chunk", "qkv: 16 mma + epilogue + K issue", "qkv: block barrier", "self-attn: K loads + scores", "self-attn: softmax", "self-attn: V loads + PV", "self-attn: tail + context send", "wait context 1", "out-proj 1 tiles + y send", "wait y 1",
+LAYER = ["qkv: wait for the weight chunk", "qkv: 16 mma + epilogue + K issue", "qkv: block barrier", "self-attn: K/V blocks, online softmax, P.V", "self-attn: context send + append + prefetch", "wait context 1", "out-proj 1 tiles + y send", "wait y 1",
          "layernorm 1 + sync", "cross-q tiles + sync", "cross-attention + context send", "wait context 2",
          "out-proj 2 tiles + y send", "wait y 2", "layernorm 2 + sync", "linear1 tiles + hidden send", "wait hidden",
          "linear2 tiles + y send", "wait y 3", "layernorm 3 + sync", "next layer: bias wait"]
