@@ -46,6 +46,7 @@ SIGNATURES = {
     "hmocr_generate_host_u8": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hmocr_last_timings": (_i, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "hmocr_gemm_f16": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _i, _p]),
+    "hmocr_swin_mlp": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "hmocr_layernorm": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
     "hmocr_patch_embed": (_i, [_p, _i, _p, _p, _p, _p, _p, _p]),
     "hmocr_patch_merge_ln": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),

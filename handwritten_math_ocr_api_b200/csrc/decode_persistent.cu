@@ -31,12 +31,13 @@
 // Attention.  One warp per (row, head), on tensor cores: S = K q as mma.m16n8k16 with 16 cached keys
 // as the M operand, softmax in fp32 on ex2, then O = V^T p with 16 head dims as the M operand.  Both caches are
 // fp16 and stored in the REGISTER ORDER of the mma A operand (fragment-major blocks of 32 keys x 32 dims = 2 KB),
-// so a fragment is one coalesced 16-byte load per lane; probabilities pass through an 80-word per-warp shared
-// buffer.  One 2 KB block of K (then V) is in flight per warp; a last block with <= 16 keys is read as 1 KB.
+// so a fragment is one coalesced 16-byte load per lane.  One pass with an online softmax: the K and the V block of
+// the same 32 keys are in flight together (4 KB per warp), the probabilities reach the P operand by two shuffles
+// per 16 keys (no shared memory); a last block with <= 16 keys is read as 1 KB.
 // The cache rows of the NEXT layer are pulled into L2 (cp.async.bulk.prefetch.L2) one layer ahead; history
 // loads carry L2 evict_first, the weight stream and the memory K/V evict_last (they are re-read every step).
 //
-// Occupancy is part of the design: ~104 KB of shared memory (greedy, T <= 160) and <= 128 registers, so TWO CTAs (of
+// Occupancy is part of the design: ~104 KB of shared memory and <= 128 registers, so TWO CTAs (of
 // different clusters) share an SM; B=256 runs as 32 clusters in a single wave.
 #include <cuda_fp16.h>
 
@@ -66,7 +67,6 @@ struct Smem {
   alignas(16) float stg[4][16][9];          // staging of GEMM tiles [task][feature][row] (hidden: fp16 [8][72])
   alignas(16) float x32s[R][32];            // fp32 residual stream, this CTA's 32-feature slice only
   alignas(16) __half qh[R][HD];             // this head's scaled query (fp16 mma operand)
-  alignas(16) uint32_t pbuf[NW][128];       // per-warp softmax probabilities in P-operand order (half2 words)
   alignas(16) __half knew[R][HD];           // this step's key / value of head c (appended to the caches after use)
   alignas(16) __half vnew[R][HD];
   Partial part[CL][R];                      // per-CTA argmax / sum-exp partials (gathered)
@@ -242,19 +242,10 @@ __device__ __forceinline__ int vfrag_half(int key_in_blk, int d) {      // half 
 // One query row of one head against n cached keys, on tensor cores.
 //   scores:  S[16 keys x 8] = K[16 keys x 32 dims] . q      (q replicated in all 8 columns; two k-steps)
 //   output:  O[16 dims x 8] = Vt[16 dims x 16 keys] . p     (p replicated in all columns; two m-tiles)
-// q is pre-scaled by log2(e)/sqrt(32): the softmax runs on ex2.  Probabilities go through a 64-byte per
-// block shared buffer in P-operand order.
-// Keys come in blocks of 32 (2 KB of K and 2 KB of V).  Four register slots of one block each form the
-// load pipeline: attend_issue() puts the first four K blocks in flight (it is called BEFORE the block
-// barrier that publishes q, so the barrier wait hides part of the latency); attend_mma() consumes K block
-// b from slot b % 4 and immediately re-arms the slot with K block b+4 or, once the slot has seen its
-// last K block, with V block b % 4 - so the V loads fly while the remaining scores and the softmax are
-// computed.
+// q is pre-scaled by log2(e)/sqrt(32): the softmax runs on ex2.  Keys come in blocks of 32 (2 KB of K and 2 KB of V).
 // Result: out[j] = context of dim 4*g4 + j (identical in the 4 lanes that share g4).
 // If NEW, one more key/value (this step's own, still in shared memory) is folded in on CUDA cores, so the
 // attention never waits for its own cache append to travel through L2.
-template <int KV_SLOTS>
-struct KvSlots { uint4 r[KV_SLOTS][4]; };
 
 // Block b of a (layer, row, head) region holding `n` keys in all.  In both layouts the first 1 KB of a block is its
 // first 16 keys (K: tile 0, V: k-step 0), so a last block with <= 16 keys is read as 1 KB, not 2 (the other half is
@@ -274,124 +265,15 @@ __device__ __forceinline__ void load_block(const uint4* base, int b, int n, uint
 }
 // bytes of a region that hold its first `keys` keys at 1 KB granularity (for the L2 prefetch)
 __device__ __forceinline__ int region_bytes(int keys) { return ((keys + 15) >> 4) * 1024; }
-template <int NB, int KV_SLOTS, bool MEM>
-__device__ __forceinline__ void attend_issue(const __half* Kc, int n, int lane, KvSlots<KV_SLOTS>& kv) {
-  const int nb = (n + 31) >> 5;
-  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;       // + 128 * block + 32 * fragment
-#pragma unroll
-  for (int b = 0; b < KV_SLOTS && b < NB; ++b)
-    if (b < nb) load_block<MEM>(Kl, b, n, kv.r[b]);
-}
 // If COPY (beam search), every consumed history block is also stored to (Kd, Vd): the destination row of the
 // other cache set - the parent gather of the beam reorder rides on the attention loads.
 __device__ __forceinline__ void store_block(uint4* base, int b, const uint4 (&d)[4]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) __stcg(base + 128 * b + 32 * u, d[u]);
 }
-template <int NB, bool NEW, bool COPY, int KV_SLOTS, bool MEM>
-__device__ __forceinline__ void attend_mma(const __half* qh, const __half* Kc, const __half* Vc, int n,
-                                           const __half* knew, const __half* vnew, uint32_t* pbuf, int lane,
-                                           KvSlots<KV_SLOTS>& kv, float (&out)[4], long long* tr, __half* Kd = nullptr,
-                                           __half* Vd = nullptr) {
-  const int g4 = lane >> 2, t4 = lane & 3;
-  const uint2 q0 = *reinterpret_cast<const uint2*>(qh + 4 * t4), q1 = *reinterpret_cast<const uint2*>(qh + 16 + 4 * t4);
-  const int nb = (n + 31) >> 5;
-  const uint4* Kl = reinterpret_cast<const uint4*>(Kc) + lane;
-  const uint4* Vl = reinterpret_cast<const uint4*>(Vc) + lane;
-  float snew = -INFINITY;
-  if (NEW) {
-    const uint4 kn = *reinterpret_cast<const uint4*>(knew + t4 * 8), qn = *reinterpret_cast<const uint4*>(qh + t4 * 8);
-    const uint32_t qw[4] = {qn.x, qn.y, qn.z, qn.w}, kw[4] = {kn.x, kn.y, kn.z, kn.w};
-    float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[i]));
-      const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&kw[i]));
-      a = fmaf(qf.x, kf.x, a); a = fmaf(qf.y, kf.y, a);
-    }
-    a += __shfl_xor_sync(0xffffffffu, a, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
-    snew = a;
-  }
-  float sc[NB * 4];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    if (b < nb) {                                                   // warp-uniform
-      uint4(&d)[4] = kv.r[b % KV_SLOTS];
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(c, d[2 * tile].x, d[2 * tile].y, d[2 * tile].z, d[2 * tile].w, q0.x, q0.y);
-        mma_f16(c, d[2 * tile + 1].x, d[2 * tile + 1].y, d[2 * tile + 1].z, d[2 * tile + 1].w, q1.x, q1.y);
-        const int key = 32 * b + 16 * tile + g4;
-        sc[4 * b + 2 * tile] = (key < n) ? c[0] : -INFINITY;
-        sc[4 * b + 2 * tile + 1] = (key + 8 < n) ? c[2] : -INFINITY;
-      }
-      if (COPY && Kd != nullptr) store_block(reinterpret_cast<uint4*>(Kd) + lane, b, d);
-      if (b + KV_SLOTS < NB && b + KV_SLOTS < nb) load_block<MEM>(Kl, b + KV_SLOTS, n, d);       // next K block of this slot ...
-      else load_block<MEM>(Vl, b % KV_SLOTS, n, d);                                // ... or its first V block (b & 3 < nb here)
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) sc[4 * b + u] = -INFINITY;
-    }
-  }
-  if (tr) tr[0] = clock64();
-  float m = snew;
-#pragma unroll
-  for (int i = 0; i < NB * 4; ++i) m = fmaxf(m, sc[i]);
-#pragma unroll
-  for (int o = 4; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float den = 0.f;
-  uint32_t* pw = pbuf + (g4 & 3) * 2 + (g4 >> 2);                   // this lane's word of each 8-word k-step
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    if (b < nb) {
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        const __half2 ph = __floats2half2_rn(ex2f(sc[4 * b + 2 * tile] - m), ex2f(sc[4 * b + 2 * tile + 1] - m));
-        const float2 pf = __half22float2(ph);                       // normalise with the rounded weights
-        den += pf.x + pf.y;
-        pw[16 * b + 8 * tile] = *reinterpret_cast<const uint32_t*>(&ph);   // same word from the 4 lanes of a group
-      }
-    }
-  }
-  __syncwarp();
-  if (tr) tr[1] = clock64();
-  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    if (b < nb) {
-      uint4(&d)[4] = kv.r[b % KV_SLOTS];
-      const uint2 p0 = *reinterpret_cast<const uint2*>(pbuf + 16 * b + 2 * t4);
-      const uint2 p1 = *reinterpret_cast<const uint2*>(pbuf + 16 * b + 8 + 2 * t4);
-      mma_f16(acc0, d[0].x, d[0].y, d[0].z, d[0].w, p0.x, p0.y);
-      mma_f16(acc1, d[1].x, d[1].y, d[1].z, d[1].w, p0.x, p0.y);
-      mma_f16(acc0, d[2].x, d[2].y, d[2].z, d[2].w, p1.x, p1.y);
-      mma_f16(acc1, d[3].x, d[3].y, d[3].z, d[3].w, p1.x, p1.y);
-      if (COPY && Vd != nullptr) store_block(reinterpret_cast<uint4*>(Vd) + lane, b, d);
-      if (b + KV_SLOTS < NB && b + KV_SLOTS < nb) load_block<MEM>(Vl, b + KV_SLOTS, n, d);
-    }
-  }
-#pragma unroll
-  for (int o = 4; o < 32; o <<= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-  if (tr) tr[2] = clock64();
-  if (NEW) {
-    const float pn = __half2float(__float2half_rn(ex2f(snew - m)));
-    den += pn;
-    const uint2 vn = *reinterpret_cast<const uint2*>(vnew + 4 * g4);
-    const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&vn.x));
-    const float2 v23 = __half22float2(*reinterpret_cast<const __half2*>(&vn.y));
-    acc0[0] = fmaf(pn, v01.x, acc0[0]); acc0[2] = fmaf(pn, v01.y, acc0[2]);
-    acc1[0] = fmaf(pn, v23.x, acc1[0]); acc1[2] = fmaf(pn, v23.y, acc1[2]);
-  }
-  const float inv = __fdividef(1.0f, den);
-  out[0] = acc0[0] * inv; out[1] = acc0[2] * inv; out[2] = acc1[0] * inv; out[3] = acc1[2] * inv;
-  __syncwarp();                                                     // pbuf may be rewritten by the next call
-}
-
-// ---- one-pass (online-softmax) variant ------------------------------------------------------------------
-// The two-pass form above keeps ONE 2 KB block in flight per warp: every K block, then every V block, pays a full
-// L2 round trip behind the previous one, and the softmax between them overlaps nothing.  Here the K and the V block
+// One pass, online softmax.  (The two-pass form of round 1 - all scores, softmax, then P.V - kept ONE 2 KB block in
+// flight per warp: every K block, then every V block, paid a full L2 round trip behind the previous one, and the
+// softmax between them overlapped nothing: 7.2k cycles per layer at step 100, now 5.9k.)  The K and the V block
 // of the same 32 keys travel TOGETHER (two register slots, 4 KB in flight per warp) and every block is finished
 // before the next: scores -> running maximum -> probabilities -> accumulators rescaled -> P.V.  The next K block
 // is requested as soon as the scores of this one exist, the next V block as soon as its P.V is issued, so the
@@ -564,11 +446,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 2)
 decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   constexpr bool BEAM = KB > 0;
   const int dev_flags = DEV ? p.flags : 0;
-  // K/V register pipeline depth (blocks of 32 keys in flight per warp).  ONE slot beats two, three and four (greedy B=256
-  // decode: 16.6 / 16.7 / 17.1 / 17.65 ms; beam 5 at 64 images: 266 vs 290 us per step with four): the 16 warps of an SM
-  // already cover the latency - the attention phases are bound by the L2 -> SM ingest of the K/V bytes - and every slot
-  // costs 16 live registers at the 128-register cap (one slot: no spills in the greedy kernel, 4 bytes in the beam kernel).
-  constexpr int KVS = 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -107,6 +107,7 @@ struct hmocr_engine {
   int dbg_flags = 0;                  // DecPersistParams::flags
   int conv_impl = 0;                  // ResNet trunk: 0 = implicit GEMM (TMA patches), 1 = explicit im2col + GEMM
   int force_beam_kernel = 0;          // run beam = 1 through the beam-search kernel (A/B test against greedy)
+  int mlp_fused = 1;                  // Swin stages 1/2: fc1 + GELU + fc2 + residual in one kernel (0 = two GEMM launches)
 
   // Scratch buffers, addressed by name; any (re)placement invalidates the captured graphs (ws_epoch).
   //  * caller-owned (SURVEY.md 8b "Ownership"): hmocr_set_workspace hands the engine ONE buffer (a torch tensor on the
@@ -378,12 +379,16 @@ int encode_impl(hmocr_engine* e, const float* images, int B, float* enc32, h16* 
       ep.residual = x; ep.ldr = C; ep.out_f32 = x; ep.ld32 = C;
       HM_TRY(run_lin(st, ctx, C, rows, sb.proj, ep));
       HM_TRY(layernorm(st, x, rows, C, sb.n2.g, sb.n2.b, xn, nullptr));
-      GemmEpilogue e1;
-      e1.act = 1; e1.out_f16 = hid; e1.ld16 = 4 * C;
-      HM_TRY(run_lin(st, xn, C, rows, sb.fc1, e1));
-      GemmEpilogue e2;
-      e2.residual = x; e2.ldr = C; e2.out_f32 = x; e2.ld32 = C;
-      HM_TRY(run_lin(st, hid, 4 * C, rows, sb.fc2, e2));
+      if (e->mlp_fused && swin_mlp_supported(C)) {       // the [rows, 4C] hidden tensor never reaches HBM
+        HM_TRY(swin_mlp(st, xn, rows, C, sb.fc1.w, sb.fc1.b, sb.fc2.w, sb.fc2.b, x));
+      } else {
+        GemmEpilogue e1;
+        e1.act = 1; e1.out_f16 = hid; e1.ld16 = 4 * C;
+        HM_TRY(run_lin(st, xn, C, rows, sb.fc1, e1));
+        GemmEpilogue e2;
+        e2.residual = x; e2.ldr = C; e2.out_f32 = x; e2.ld32 = C;
+        HM_TRY(run_lin(st, hid, 4 * C, rows, sb.fc2, e2));
+      }
     }
     if (s < 3) {
       const Merge& m = e->merges[s];
@@ -1265,6 +1270,10 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     gemm_set_debug(value);
   } else if (n == "force_beam_kernel") {
     e->force_beam_kernel = value != 0;
+  } else if (n == "mlp_fused") {
+    HM_CHECK(value == 0 || value == 1, "mlp_fused must be 0 (fc1 and fc2 as two GEMM launches) or 1 (one kernel)");
+    if (e->mlp_fused != value) ++e->ws_epoch;            // captured encoder graphs hold the other schedule
+    e->mlp_fused = value;
   } else {
     HM_CHECK(false, "unknown option '%s'", name);
   }
@@ -1448,6 +1457,13 @@ HM_API int hmocr_gemm_f16(const void* a, int lda, int M, int K, const void* w, i
   epi.ln_gamma = ln_gamma; epi.ln_beta = ln_beta;
   return gemm_f16(static_cast<cudaStream_t>(stream), static_cast<const h16*>(a), lda, M, K,
                    static_cast<const h16*>(w), N, epi, force_bn);
+}
+
+HM_API int hmocr_swin_mlp(const void* xn, int M, int C, const void* w1, const float* b1, const void* w2, const float* b2,
+                          float* x, void* stream) {
+  HM_CHECK(xn != nullptr && w1 != nullptr && w2 != nullptr && x != nullptr, "null buffer");
+  return swin_mlp(static_cast<cudaStream_t>(stream), static_cast<const h16*>(xn), M, C, static_cast<const h16*>(w1), b1,
+                  static_cast<const h16*>(w2), b2, x);
 }
 
 HM_API int hmocr_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, void* out_f16,

@@ -811,6 +811,10 @@ int gemm_conv_f16(cudaStream_t stream, const h16* x, int B, int H, int W, int Ci
 }
 
 void gemm_set_debug(int v) { g_gemm_dbg = v; }
+int gemm_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  return get_tensor_map(ptr, rows, cols, ld, box_rows, out);
+}
+int gemm_num_sms() { return num_sms(); }
 
 int gemm_init() {
   // per DEVICE: the shared-memory opt-in of a kernel is an attribute of the function on one device

@@ -32,6 +32,10 @@ int gemm_conv_f16(cudaStream_t stream, const h16* x, int B, int H, int W, int Ci
                   const h16* Wt, int N, const GemmEpilogue& epi);
 
 int gemm_init();
+// 2-D fp16 tensor map (K-major rows, 128B swizzle, box = 64 columns x box_rows rows), cached per (ptr, shape); for the
+// other tcgen05 kernels of the library (swin_mlp.cu).  gemm_init() must have run on this device.
+int gemm_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out);
+int gemm_num_sms();
 void gemm_set_debug(int v);   // timing experiments only (see gemm.cu)   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
 
 }  // namespace hmocr

@@ -14,6 +14,12 @@ int patch_embed(cudaStream_t st, const float* images, int B, const float* w, con
 int window_attention(cudaStream_t st, const h16* qkv, const float* qkv_bias, const float* rel_bias, int B,
                      int H, int W, int C, int heads, int shift, h16* ctx);       // tensor-core (swin_attention.cu)
 
+// fused MLP of a Swin block (swin_mlp.cu): x <- x + fc2(GELU(fc1(xn) + b1)) + b2, hidden tile kept in TMEM / shared
+// memory.  xn fp16 [M, C] (= LayerNorm2(x)), w1 fp16 [4C, C], w2 fp16 [C, 4C], x fp32 [M, C] in place.  C in {96, 192}.
+bool swin_mlp_supported(int C);
+int swin_mlp(cudaStream_t st, const h16* xn, int M, int C, const h16* w1, const float* b1, const h16* w2,
+             const float* b2, float* x);
+
 // ---- decoder -------------------------------------------------------------------------------------
 struct DecodeState {      // device-resident control block of one generate call
   int step;               // current decode step t (position of the token being fed)

@@ -152,6 +152,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) window_attn_mma_kernel(const h1
 
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
+      // a tile of 16 query slots that are ALL padding (the window rows below the image: half of every bottom window at
+      // stages 1 / 2, a quarter of every window at stage 3, half at stage 4) produces nothing that is written
+      {
+        const int pq = mt * 16 + (lane & 15);
+        if (!__any_sync(0xffffffffu, pq < WN && s.tok[pq] >= 0)) continue;
+      }
       uint32_t aq[2][4];
       const uint32_t qa = mt < 3 ? q_lane + mt * 16 * (TP * 2) : q_last;
       ldsm4(qa, aq[0]);

@@ -188,6 +188,12 @@ int hmocr_gemm_f16(const void* a_dev, int lda, int M, int K, const void* w_dev, 
                     int act, const float* residual_dev, int ldr, float* out_f32_dev, int ld32, void* out_f16_dev,
                     int ld16, const float* ln_gamma_dev, const float* ln_beta_dev, int force_bn, void* stream);
 
+/* MLP of a Swin block fused with its residual add (torchvision swin_transformer.py:444, 455):
+ * x <- x + fc2(GELU(fc1(xn))), xn fp16 [M,C] (= norm2(x)), w1 fp16 [4C,C], w2 fp16 [C,4C], x f32 [M,C] in place.
+ * C in {96, 192} (Swin-T stages 1 and 2); the hidden tile stays in TMEM / shared memory. */
+int hmocr_swin_mlp(const void* xn_dev, int M, int C, const void* w1_dev, const float* b1_dev, const void* w2_dev,
+                   const float* b2_dev, float* x_dev, void* stream);
+
 /* nn.LayerNorm over the last axis: x f32 [rows, C] -> fp16 and/or f32 */
 int hmocr_layernorm(const float* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
                     void* out_f16_dev, float* out_f32_dev, void* stream);

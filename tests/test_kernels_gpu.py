@@ -90,6 +90,49 @@ def test_gemm_fused_layernorm(N, K):
     assert (o16.float() - ref).abs().max().item() < 5e-2
 
 
+@pytest.mark.parametrize("C_,M", [(96, 3840), (96, 128), (96, 1), (96, 130), (96, 40000), (192, 960), (192, 200), (192, 30000)])
+def test_swin_mlp_fused(C_, M):
+    """x <- x + fc2(GELU(fc1(xn))) in ONE kernel (hidden tile in TMEM / shared memory) against (a) plain torch fp32
+    with the hidden activations rounded to fp16 where the kernel rounds them, (b) the two-GEMM path of the library
+    (same arithmetic, same rounding points: equal up to fp32 summation order).  M covers one tile, a ragged last
+    tile, a single row and many tiles per CTA (persistence, barrier phase wrap-around)."""
+    lib, L = _lib()
+    xn = _rand(M, C_, seed=30).half()
+    w1 = _rand(4 * C_, C_, scale=C_ ** -0.5, seed=31).half()
+    w2 = _rand(C_, 4 * C_, scale=(4 * C_) ** -0.5, seed=32).half()
+    b1, b2 = 0.3 * _rand(4 * C_, seed=33), 0.3 * _rand(C_, seed=34)
+    x0 = _rand(M, C_, seed=35) * 2
+    hid = torch.nn.functional.gelu(xn.float() @ w1.float().t() + b1).half()
+    ref = x0 + hid.float() @ w2.float().t() + b2
+    x = x0.clone()
+    L.check(lib.hmocr_swin_mlp(P(xn), M, C_, P(w1), P(b1), P(w2), P(b2), P(x), S()), "swin_mlp")
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    err = (x - ref).abs().max().item()
+    assert err < 3e-3, err
+    # the two-launch path: fc1 + GELU -> fp16 hidden in HBM, fc2 + residual in place
+    _, h16 = gemm(xn, w1, bias=b1, act=1, out_f32=False, out_f16=True)
+    x2 = x0.clone()
+    L.check(lib.hmocr_gemm_f16(P(h16), 4 * C_, M, 4 * C_, P(w2), C_, P(b2), 0, P(x2), C_, P(x2), C_, None, 0, None, None,
+                               0, S()), "gemm")
+    torch.cuda.synchronize()
+    assert (x - x2).abs().max().item() < 1e-3
+    # a second call on the same buffers (tensor-map cache, barrier state of a fresh launch) gives the same result
+    x3 = x0.clone()
+    L.check(lib.hmocr_swin_mlp(P(xn), M, C_, P(w1), P(b1), P(w2), P(b2), P(x3), S()), "swin_mlp")
+    torch.cuda.synchronize()
+    assert torch.equal(x, x3)
+
+
+def test_swin_mlp_rejects_other_widths():
+    lib, L = _lib()
+    xn = _rand(8, 384).half()
+    w1, w2 = _rand(1536, 384).half(), _rand(384, 1536).half()
+    b1, b2, x = _rand(1536), _rand(384), _rand(8, 384)
+    rc = lib.hmocr_swin_mlp(P(xn), 8, 384, P(w1), P(b1), P(w2), P(b2), P(x), S())
+    assert rc != 0 and b"unsupported" in lib.hmocr_last_error()
+
+
 def test_gemm_rejects_bad_shapes():
     lib, L = _lib()
     a = _rand(8, 64).half()

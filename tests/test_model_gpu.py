@@ -64,6 +64,25 @@ def test_encoder_is_batch_independent(model, golden_src):
     assert torch.equal(a[1:2], b)
 
 
+def test_encoder_fused_mlp_matches_the_two_launch_path(model, golden_src):
+    """Option ``mlp_fused`` (default 1: fc1 + GELU + fc2 + residual of Swin stages 1 / 2 in one kernel, the hidden
+    tile never in HBM) against the same encoder with fc1 and fc2 as two GEMM launches: same rounding points, so the
+    features agree to fp32 summation-order noise; both stay inside the tolerance against the reference's golden."""
+    imgs = _images(golden_src).cuda()
+    fused = model.encoder(imgs).clone()
+    model.set_option("mlp_fused", 0)
+    try:
+        plain = model.encoder(imgs).clone()
+    finally:
+        model.set_option("mlp_fused", 1)
+    assert (fused - plain).abs().max().item() < 5e-3      # fp32 summation order, amplified by the fp16 roundings downstream
+    for f in (fused, plain):
+        assert np.abs(f.cpu().numpy() - golden_src["features"]).max() < FEAT_TOL
+    big = imgs.repeat(9, 1, 1, 1)[:33]                        # > 32 images: eager launches, ragged last tile at stage 2
+    assert torch.equal(model.encoder(big)[:4], model.encoder(big)[:4])
+    assert (model.encoder(big)[:4] - fused).abs().max().item() < 5e-3
+
+
 def test_encoder_stage_by_stage(model, dsd, cfg, golden_src):
     """Localises an encoder error: every Swin stage of the engine, rebuilt from its exported kernels (patch embed,
     LayerNorm, qkv / proj / MLP GEMMs, window attention, patch merging), against the oracle's stage outputs."""

@@ -172,6 +172,7 @@ def test_sequence_agreement_1024_images(cfg, case):
     dsd = {k: v.cuda() for k, v in sd.items()}
     m = _engine(sd, cfg)
     same = same_decode_only = total = 0
+    max_logit = 0.0
     div_margins, div_margins_e2e, top1, small = [], [], [], []
 
     def upto_eos(row):
@@ -187,6 +188,7 @@ def test_sequence_agreement_1024_images(cfg, case):
         # decode only: the oracle on the ENGINE's features
         ys2, lg2 = odec.greedy_cached(m.encoder(imgs), dsd, cfg, max_len=150, return_logits=True)
         top1.append(torch.softmax(lg, -1).max(-1).values.flatten().cpu())
+        max_logit = max(max_logit, float(lg.abs().max()))
         for ref, lgs, bucket, which in ((ys, lg, div_margins_e2e, 0), (ys2, lg2, div_margins, 1)):
             top2 = lgs.topk(2, -1).values
             margin = (top2[..., 0] - top2[..., 1]).cpu()
@@ -206,7 +208,7 @@ def test_sequence_agreement_1024_images(cfg, case):
                 bucket.append(float(margin[r, min(c, margin.shape[1]) - 1]))
         total += 256
     top1 = torch.cat(top1)
-    res = {"fc_gain": fc_gain, "peak": peak, "images": total, "identical_end_to_end": same,
+    res = {"fc_gain": fc_gain, "peak": peak, "images": total, "oracle_max_abs_logit": max_logit, "identical_end_to_end": same,
            "identical_decode_only": same_decode_only, "frac_end_to_end": same / total,
            "frac_decode_only": same_decode_only / total,
            "oracle_top1_prob_median": float(top1.median()), "oracle_top1_prob_p10": float(top1.quantile(0.1)),
@@ -214,8 +216,10 @@ def test_sequence_agreement_1024_images(cfg, case):
            "divergence_margin_max_decode_only": max(div_margins) if div_margins else 0.0,
            "divergence_margin_max_end_to_end": max(div_margins_e2e) if div_margins_e2e else 0.0}
     _record(f"agreement_{case}", res)
-    # a near-tie scales with the logits: the absolute error of fp16 arithmetic grows with the logit scale
-    assert (max(div_margins) if div_margins else 0.0) < TIE_MARGIN * fc_gain / 4.0
+    # a near-tie scales with the logits: the absolute error of fp16 operands (2^-11 relative) grows with the logit
+    # magnitude - TIE_MARGIN (2e-2) is for the random-init checkpoint, whose largest |logit| is ~20; the peaked
+    # checkpoints reach |logit| > 100 (oracle_max_abs_logit in the record)
+    assert (max(div_margins) if div_margins else 0.0) < TIE_MARGIN * max(1.0, max_logit / 20.0)
     assert same / total >= floor
 
 
