@@ -254,8 +254,9 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bb = bp[q];
-          float v0 = __uint_as_float(r[4 * q]) + bb.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y;
-          float v2 = __uint_as_float(r[4 * q + 2]) + bb.z, v3 = __uint_as_float(r[4 * q + 3]) + bb.w;
+          float v0, v1, v2, v3;
+          upk2(add2(pk2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), pk2(bb.x, bb.y)), v0, v1);
+          upk2(add2(pk2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), pk2(bb.z, bb.w)), v2, v3);
           gelu_erf2(v0, v1);
           gelu_erf2(v2, v3);
           h[2 * q] = pack16(v0, v1);

@@ -84,3 +84,31 @@ def test_evaluation_metrics_follow_the_reference_formula():
     assert truth_string([1, 3, 4, 4, 2, 0, 0], 5, idx2char) == "a b b"
     s = summarize([{"is_correct": True, "cer": 0.0}, {"is_correct": False, "cer": 0.5}])
     assert s == {"accuracy": 0.5, "avg_cer": 0.25, "total_samples": 2}
+
+
+def test_gelu_polynomial_of_the_kernels_is_the_exact_erf_form():
+    """The GEMM / fused-MLP epilogues evaluate nn.GELU() (erf form, torchvision swin_transformer.py:444) as
+    max(x,0) - |x| 2^q(|x|) with the degree-5 polynomial whose coefficients stand in csrc/common.cuh.  Re-evaluated here
+    in float32 Horner form straight from the header text: within 2e-6 of x Phi(x) everywhere (no clamp of |x| - the
+    polynomial must drive 2^q to zero by itself), within one fp16 ulp of the value (the hidden activations are stored
+    as fp16), relative error < 2e-5 near zero."""
+    import math
+    import numpy as np
+    text = open(os.path.join(ROOT, "handwritten_math_ocr_api_b200", "csrc", "common.cuh")).read()
+    c = {int(k): float(v) for k, v in re.findall(r"GELU_C(\d) = (-?[0-9.]+e[+-]\d+)f", text)}
+    assert sorted(c) == [1, 2, 3, 4, 5] and c[5] < 0          # negative leading coefficient: q -> -inf, 2^q -> 0
+    xs = np.concatenate([np.linspace(-12, 12, 400001), np.linspace(-60000, 60000, 20001)]).astype(np.float32)
+    a = np.abs(xs)
+    q = np.full_like(a, np.float32(c[5]))
+    for k in (4, 3, 2, 1):
+        q = (q * a + np.float32(c[k])).astype(np.float32)
+    q = (q * a + np.float32(-1.0)).astype(np.float32)
+    with np.errstate(over="ignore", under="ignore"):
+        out = np.maximum(xs, 0) - a * np.exp2(q)
+    ref = np.array([0.5 * x * (1.0 + math.erf(x / math.sqrt(2.0))) for x in xs.astype(np.float64)])
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < 2e-6
+    ulp16 = 2.0 ** (np.floor(np.log2(np.maximum(np.abs(ref), 2.0 ** -14))) - 10)
+    assert (np.abs(out - ref) / ulp16).max() < 1.0
+    small = (a < 1) & (ref != 0)
+    assert (np.abs(out - ref)[small] / np.abs(ref[small])).max() < 2e-5

