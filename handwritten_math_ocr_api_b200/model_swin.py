@@ -385,7 +385,8 @@ class FormulaRecognitionModel:
         return packed, lengths
 
     def set_option(self, name: str, value: int) -> None:
-        """Engine options of ``hmocr_set_option`` (``decode_impl``, ``steps_per_launch``)."""
+        """Engine options of ``hmocr_set_option`` (``decode_impl``, ``steps_per_launch``, ``encoder_graph``, ``mlp_fused``, ...:
+        include/hmocr.h lists them)."""
         _lib.check(self._eng.lib.hmocr_set_option(self._eng.handle, name.encode(), int(value)), "hmocr_set_option")
         # options change which scratch buffers a call uses (step graph / beam kernel / tracing): plan again
         self._reserved = {"gen": (0, 0, 0), "tf": (0, 0)}

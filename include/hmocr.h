@@ -76,7 +76,10 @@ int hmocr_finalize_weights(hmocr_engine* e);
  *                       batches of up to 32 images (launch-bound regime; first call at a batch size runs eagerly,
  *                       the second captures); 0 = always launch kernel by kernel
  *   "conv_impl"         ResNet-18 variant: 0 = convolutions as implicit GEMMs, the patches built by 4-D TMA
- *                       loads (default); 1 = explicit im2col matrix + GEMM (kept for A/B tests) */
+ *                       loads (default); 1 = explicit im2col matrix + GEMM (kept for A/B tests)
+ *   "mlp_fused"         Swin stages 1 / 2: 1 (default) = fc1 + GELU + fc2 + residual in one kernel, the hidden tile in
+ *                       TMEM / shared memory (hmocr_swin_mlp); 0 = two GEMM launches with the hidden tensor in HBM
+ *                       (kept for A/B tests) */
 int hmocr_set_option(hmocr_engine* e, const char* name, int value);
 /* Developer aid: with option "trace_step" = t >= 0 the persistent decode kernel records clock64()
  * of (cluster 0, CTA 0, thread 0) at every phase boundary of decode step t; this copies the first
