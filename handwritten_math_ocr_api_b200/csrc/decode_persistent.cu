@@ -694,6 +694,9 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
         }
       }
       TR();
+      // the memory K / V of cross-attention depend on nothing in this step: requested here, they travel under the
+      // out-projection, LayerNorm 1 and the cross-query projection
+      attend_issue2<true>(p.memk + (size_t)l * m_layer + m_row, p.memv + (size_t)l * m_layer + m_row, p.mem_len, lane, kv);
       // ---- x = LN1(x + out_proj(ctx)) ---------------------------------------------------------------
       xwait(X_CTX, 0u, XB_CTX);
       TR();
@@ -735,7 +738,6 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
       const __half* Mk = p.memk + (size_t)l * m_layer + m_row;       // (not live across the self-attention block)
       const __half* Mv = p.memv + (size_t)l * m_layer + m_row;
-      attend_issue2<true>(Mk, Mv, p.mem_len, lane, kv);
       __syncthreads();
       TR();
       {
