@@ -209,6 +209,33 @@ __device__ __forceinline__ void gemm16(const uint8_t* W, const __half* X, int la
   for (int i = 0; i < 4; ++i) c[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
 }
 
+// The same product with the activation (B) fragments already in registers: the vocabulary projection runs five weight
+// chunks per warp against the SAME 8 x 256 activations, and at two CTAs per SM that phase is bound by the shared-memory
+// port (TMA writes + ldmatrix reads of the weights + the activation re-reads) - loading the 32 fragment registers once
+// per step instead of once per chunk takes a fifth of the port traffic away.  Same mma order as gemm16: same bits.
+template <int PB>
+__device__ __forceinline__ void load_bfrags(const __half* X, int lane, uint32_t (&bf)[8][4]) {
+  const uint32_t b_addr = smem_u32(X) + ((lane & 7) * PB + (lane >> 3) * 8) * 2;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) ldsm_x4(b_addr + kk * 64, bf[kk]);
+}
+__device__ __forceinline__ void gemm16_pre(const uint8_t* W, const uint32_t (&bf)[8][4], int lane, float (&c)[4]) {
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const uint32_t a_addr = smem_u32(W) + ((lane & 15) * PD + (lane >> 4) * 8) * 2;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    uint32_t a0[4], a1[4];
+    ldsm_x4(a_addr + kk * 64, a0);
+    ldsm_x4(a_addr + kk * 64 + 32, a1);
+    mma_f16(acc[(2 * kk) & 3], a0[0], a0[1], a0[2], a0[3], bf[kk][0], bf[kk][1]);
+    mma_f16(acc[(2 * kk + 1) & 3], a1[0], a1[1], a1[2], a1[3], bf[kk][2], bf[kk][3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
+}
+
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -824,11 +851,13 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     ta.init(); tb.init();
     {
       const int j0 = (warp - g) & 7;
+      uint32_t bf[8][4];
+      load_bfrags<PD>(&s.xa[0][0], lane, bf);
 #pragma unroll 1
       for (int m = j0; m < FT; m += NW) {
         float acc[4];
         slot_wait();
-        gemm16<PD>(s.slot[warp], &s.xa[0][0], lane, acc);
+        gemm16_pre(s.slot[warp], bf, lane, acc);
         const float b0 = chunk_bias(s.slot[warp], g4), b1 = chunk_bias(s.slot[warp], g4 + 8);
         slot_release();
         const int lf = m * 16 + g4, v0 = c * cols_per_cta + lf;
