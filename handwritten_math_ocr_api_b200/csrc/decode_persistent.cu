@@ -22,6 +22,10 @@
 // re-arms the slot with its next chunk (cp.async.bulk, 8 chunks ahead in the stream).  Producer and
 // consumer of a slot are the same warp, so the ring needs no empty-barriers and no block barrier.
 //
+// The vocabulary projection (40 chunks per CTA, 5 per warp) is bound by the shared-memory port at two CTAs per SM
+// (every weight byte crosses it twice: TMA in, ldmatrix out): its activation fragments are loaded into registers
+// once per step, not once per chunk.
+//
 // Exchange.  The activations of the 8 rows are all-gathered between the 8 CTAs through distributed
 // shared memory with st.async (remote store + complete_tx on an mbarrier of the DESTINATION CTA):
 // point to point, no fence on the sender, no cluster-wide barrier; a CTA proceeds as soon as ITS
