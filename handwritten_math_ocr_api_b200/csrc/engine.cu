@@ -893,14 +893,16 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
   return 0;
 }
 
-constexpr int ENC_GRAPH_MAX_BATCH = 32;
+constexpr int ENC_GRAPH_MAX_BATCH = 1024;
 
 int encode_any(hmocr_engine* e, const float* images, int B, float* enc32, h16* enc16, cudaStream_t st) {
   return e->cfg.encoder_arch == 1 ? encode_res18_impl(e, images, B, enc32, enc16, st) : encode_impl(e, images, B, enc32, enc16, st);
 }
 
 // Encoder of a generate() call.  Up to 32 images the encoder's ~95 kernels take a few microseconds each and the
-// time is the launches: the first call at a batch size runs them eagerly (allocations, function attributes), the
+// time is the launches; at large batches the GPU time does not care, but the HOST does: one cudaGraphLaunch instead of
+// ~95 launches per batch is what keeps eight ranks on one 16-core host from queueing behind each other (end-to-end
+// figure at 8 GPUs).  The first call at a batch size runs the kernels eagerly (allocations, function attributes), the
 // second captures them - reading from a staging copy of the images, so the graph has no caller pointers in it -
 // and every later call is one cudaGraphLaunch.  A workspace reallocation (ws_epoch) re-captures; a capture failure
 // turns the feature off for this engine.

@@ -73,8 +73,9 @@ int hmocr_finalize_weights(hmocr_engine* e);
  *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16)
  *   "force_beam_kernel" 1 = run beam == 1 through the beam-search kernel (A/B test against greedy)
  *   "encoder_graph"     1 (default) = hmocr_generate* replay the encoder's ~95 kernels as one captured CUDA graph for
- *                       batches of up to 32 images (launch-bound regime; first call at a batch size runs eagerly,
- *                       the second captures); 0 = always launch kernel by kernel
+ *                       batches of up to 1024 images (GPU-side gain in the launch-bound regime of <= 32 images, host-side
+ *                       gain beyond; first call at a batch size runs eagerly, the second captures); 0 = always launch
+ *                       kernel by kernel
  *   "conv_impl"         ResNet-18 variant: 0 = convolutions as implicit GEMMs, the patches built by 4-D TMA
  *                       loads (default); 1 = explicit im2col matrix + GEMM (kept for A/B tests)
  *   "mlp_fused"         Swin stages 1 / 2: 1 (default) = fc1 + GELU + fc2 + residual in one kernel, the hidden tile in
