@@ -44,6 +44,7 @@ SIGNATURES = {
     "hmocr_preprocess_image_u8": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "hmocr_preprocess_cv2_u8": (_i, [_p, _p, _i, _i, _p, _p]),
     "hmocr_generate_host_u8": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "hmocr_last_decode_steps": (_i, [_p, C.POINTER(C.c_int32)]),
     "hmocr_last_timings": (_i, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "hmocr_gemm_f16": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _i, _p]),
     "hmocr_swin_mlp": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),

@@ -84,6 +84,7 @@ struct Smem {
   int bfin[R], bsrc[R];
   alignas(8) uint64_t full[NW];
   alignas(8) uint64_t xbar[5];              // exchange barriers: context, y, hidden, partials, top-K lists
+  int stop_flag;                            // rank 0's reading of "every row has finished" at kernel entry
 };
 enum { X_CTX = 0, X_Y = 1, X_HF = 2, X_PART = 3, X_TOP = 4 };
 constexpr uint32_t XB_CTX = R * D * 2, XB_Y = R * D * 4, XB_HF = R * FF * 2, XB_PART = CL * R * sizeof(Partial);
@@ -647,8 +648,25 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
     cluster_done = true;
     for (int r = 0; r < nrows; ++r) cluster_done = cluster_done && s.bfin[r] != 0;
   }
+  // Device-side early exit (src/inference.py:23-25 breaks as soon as every row has emitted eos; the host only polls
+  // between launches, one launch behind).  "Every row has finished" is a global flag that flips at an arbitrary
+  // moment, and the 8 CTAs of a cluster must leave the step loop at the SAME step (a CTA that stayed would wait
+  // for exchanges forever): CTA rank 0 alone reads the flag - here, and once per step when it composes its arg-max
+  // partials - and the others take ITS reading (through the cluster barrier here, through the partials exchange below).
+  // What is read is the VALUE steps_executed = the reference's final ys.shape[1] - 1: a cluster that lags behind the
+  // one that finished last keeps going until it has run that many steps, so every row's columns up to `steps` hold
+  // what the reference's ys holds there (rows that finished early keep decoding in the reference too).
+  if (c == 0 && tid == 0) s.stop_flag = *reinterpret_cast<volatile int*>(&p.state->steps_executed);
   cluster_sync_all();      // every CTA of the cluster is resident and its barriers are armed before any DSMEM store
-  if (lane == 0) slot_fetch();
+  bool stop;
+  {
+    uint32_t f;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(f) : "r"(cl0 + (smem_u32(&s.stop_flag) - s_local)) : "memory");
+    stop = (int)f > 0 && t_begin >= (int)f;
+  }
+  const bool fetching = !stop;        // the weight stream was started
+  if (lane == 0 && fetching) slot_fetch();
+  int t_done = t_begin;               // steps this cluster has completed
 
   const size_t kv_rh = (size_t)p.cache_blocks * 1024;              // halves per (layer, row, head) region
   const size_t kv_layer = (size_t)p.rows * NH * kv_rh, kv_row = ((size_t)my_row * NH + c) * kv_rh;
@@ -658,7 +676,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
   const bool tracing = DEV && p.trace != nullptr && blockIdx.x == 0 && tid == 0;
   int ti = 0;
 #define TR() do { if (tracing && t == p.trace_step && ti < 1024) p.trace[ti++] = clock64(); } while (0)
-  for (int t = t_begin; t < t_end; ++t) {
+  for (int t = t_begin; t < t_end && !stop; ++t) {
     // where this step's key / value go inside the (layer, row, head) region of the fragment-major caches
     const int k_app = (t >> 5) * 512 + kfrag_word(t & 31, lane & 15);       // 32-bit word index (lanes 0..15)
     const int v_app = (t >> 5) * 1024 + vfrag_half(t & 31, lane);           // half index (lane = dim)
@@ -898,7 +916,9 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       merge_partial(a, b1);
       Partial b2 = shfl_partial(a, 2);
       merge_partial(a, b2);
-      const uint4 v = make_uint4(__float_as_uint(a.m), (uint32_t)a.idx, __float_as_uint(a.s), 0u);
+      // 4th word: rank 0's reading of steps_executed (one load instruction for the whole warp: one value)
+      const uint32_t all_done = (c == 0) ? (uint32_t)*reinterpret_cast<volatile int*>(&p.state->steps_executed) : 0u;
+      const uint4 v = make_uint4(__float_as_uint(a.m), (uint32_t)a.idx, __float_as_uint(a.s), all_done);
       const uint32_t off = smem_u32(&s.part[c][r]) - s_local, boff = smem_u32(&s.xbar[X_PART]) - s_local;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -924,6 +944,7 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
     }
     xwait(X_PART, nstep, XB_PART);
+    const bool stop_after = s.part[0][0].pad > 0 && t + 1 >= s.part[0][0].pad;      // rank 0's reading: the same value in all 8 CTAs
     TR();
     Partial a;                               // row `warp`: (max, argmax, sum-exp) over the whole vocabulary
     if (lane < CL) a = s.part[lane][warp];
@@ -1030,13 +1051,20 @@ decode_persistent_kernel(const DecPersistParams p, int t_begin, int t_end) {
       }
     }
     TR();
+    t_done = t + 1;
+    stop = stop_after;
+  }
+  if (fetching && wgi < total_chunks) {
+    // left early: this warp's slot still has a weight chunk on its way (every release re-arms the slot while the
+    // stream lasts) - the CTA must not exit under a TMA copy
+    slot_wait();
   }
   if (BEAM && c == 0 && tid < nrows) {       // hypothesis state back to HBM for the next launch / the back-track
     p.bm_score[row0 + tid] = s.bscore[tid];
     p.bm_fin[row0 + tid] = s.bfin[tid];
     p.bm_src[row0 + tid] = s.bsrc[tid];
   }
-  if (blockIdx.x == 0 && tid == 0) p.state->step = t_end;
+  if (c == 0 && tid == 0 && t_done > t_begin) atomicMax(&p.state->step, t_done);   // steps actually run (finalize: the count when no row ever finished)
   cluster_sync_all();      // no CTA exits while a peer may still address its shared memory
 }
 

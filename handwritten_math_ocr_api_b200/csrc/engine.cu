@@ -134,6 +134,7 @@ struct hmocr_engine {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // enc start, enc end, dec end, poll
   cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   DecodeState* pinned_state = nullptr;   // [2]
+  int last_poll_slot = -1;               // pinned_state slot that receives the state after the LAST persistent-kernel launch
   float last_enc_ms = 0.f, last_dec_ms = 0.f;
   bool timings_pending = false;
 };
@@ -875,6 +876,7 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
       HM_TRY(rc);
     }
     const int slot = poll_idx & 1;
+    e->last_poll_slot = slot;
     HM_CUDA(cudaMemcpyAsync(&e->pinned_state[slot], state, sizeof(DecodeState), cudaMemcpyDeviceToHost, st));
     HM_CUDA(cudaEventRecord(e->poll_ev[slot], st));
     if (poll_idx >= 1) {
@@ -1432,6 +1434,13 @@ HM_API int hmocr_generate_host_u8(hmocr_engine* e, const uint8_t* images_u8_host
   if (steps_host) HM_CUDA(cudaMemcpyAsync(steps_host, steps_d, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (score_host) HM_CUDA(cudaMemcpyAsync(score_host, score_d, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
   HM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+HM_API int hmocr_last_decode_steps(hmocr_engine* e, int32_t* steps_run) {
+  HM_CHECK(e != nullptr && steps_run != nullptr, "hmocr_last_decode_steps: null argument");
+  HM_CHECK(e->last_poll_slot >= 0 && e->pinned_state != nullptr, "no persistent-kernel decode has run on this engine");
+  *steps_run = e->pinned_state[e->last_poll_slot].step;
   return 0;
 }
 

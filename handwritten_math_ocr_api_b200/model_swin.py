@@ -391,6 +391,13 @@ class FormulaRecognitionModel:
         # options change which scratch buffers a call uses (step graph / beam kernel / tracing): plan again
         self._reserved = {"gen": (0, 0, 0), "tf": (0, 0)}
 
+    def last_decode_steps(self) -> int:
+        """Decode steps the persistent kernel executed in the last ``generate`` call (after a stream synchronise): the
+        kernel leaves its step loop on the device right after every row has emitted eos."""
+        n = C.c_int32()
+        _lib.check(self._eng.lib.hmocr_last_decode_steps(self._eng.handle, C.byref(n)), "hmocr_last_decode_steps")
+        return int(n.value)
+
     def last_timings_ms(self) -> Tuple[float, float]:
         enc, dec = C.c_float(), C.c_float()
         _lib.check(self._eng.lib.hmocr_last_timings(self._eng.handle, C.byref(enc), C.byref(dec)), "hmocr_last_timings")

@@ -179,6 +179,12 @@ int hmocr_generate_host_u8(hmocr_engine* e, const uint8_t* images_u8_host, int b
                            int64_t* tokens_host, float* logprob_host, int32_t* steps_host, float* score_host,
                            void* stream);
 
+/* Decode steps the persistent kernel actually EXECUTED in the last hmocr_generate* call on this engine (valid after the
+ * stream has been synchronised).  The reference's loop breaks right after the step at which the last row emits its
+ * first eos (src/inference.py:23-25); the kernel leaves its step loop on the device - one step after that, not at the
+ * end of the launch - so this is `steps` + 1 or 2, not `steps` rounded up to two launches. */
+int hmocr_last_decode_steps(hmocr_engine* e, int32_t* steps_run);
+
 /* Phase timings of the last hmocr_generate* call on this engine, measured with CUDA events on
  * the caller's stream (valid after the stream has been synchronised): encoder ms, decode ms. */
 int hmocr_last_timings(hmocr_engine* e, float* encoder_ms, float* decode_ms);

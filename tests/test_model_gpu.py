@@ -181,9 +181,16 @@ def test_generate_early_exit_and_padding(model, cfg, golden_src):
             assert c is None or float(golden_src["greedy_margin"][1 + r, c - 1]) < 2 * LOGIT_TOL
     else:
         assert steps == 19 and tokens.shape == (2, 20)
+    # ... and the KERNEL stops there too: it leaves its step loop on the device at most two steps after the last
+    # eos (one step for the flag to reach the cluster's rank 0, one for the cluster to act on it), it does not run
+    # its 16-step launch - and the launch the host had already queued behind it - to the end
+    torch.cuda.synchronize()
+    assert steps <= model.last_decode_steps() <= steps + 2, (steps, model.last_decode_steps())
     # max_len shorter than the sequences: length-terminated
     tokens, steps, _ = model.generate(encoder_out=feats, max_len=5)
     assert steps == 5 and tokens.shape == (2, 6) and (tokens[:, 0] == cfg.sos).all()
+    torch.cuda.synchronize()
+    assert model.last_decode_steps() == 5
 
 
 def test_generate_is_batch_invariant(model, golden_src):
