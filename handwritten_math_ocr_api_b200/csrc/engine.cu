@@ -102,7 +102,7 @@ struct hmocr_engine {
   float* dp_lnparams = nullptr;
   int dp_fc_tiles = 0, dp_chunks_per_step = 0;
   int decode_impl = 0;                // 0 = persistent cluster kernel, 1 = per-kernel step graph
-  int steps_per_launch = 16;
+  int steps_per_launch = 0;           // 0 = automatic (see generate_persistent)
   int trace_step = -1;                // >= 0: record phase-boundary clocks of that decode step
   int dbg_flags = 0;                  // DecPersistParams::flags
   int conv_impl = 0;                  // ResNet trunk: 0 = implicit GEMM (TMA patches), 1 = explicit im2col + GEMM
@@ -862,7 +862,16 @@ int generate_persistent(hmocr_engine* e, const h16* enc16, int B, int max_len, i
     HM_TRY(init_decode(st, state, tokens, max_len + 1, rows, e->cfg.sos_id, e->cfg.pad_id, finished, logprob, max_len));
   }
   if (p.trace != nullptr) HM_CUDA(cudaMemsetAsync(p.trace, 0, 1024 * sizeof(long long), st));
-  const int chunk = e->steps_per_launch > 0 ? e->steps_per_launch : 16;
+  // Steps per launch.  The kernel leaves its step loop by itself once every row has finished, so a batch whose clusters
+  // are all co-resident runs as ONE launch (no launch boundaries, no host polling).  A batch that needs several waves
+  // is cut into 16-step launches: a first-wave cluster cannot stop before the rows of the later waves have finished,
+  // so with one long launch it would run all max_len steps before the second wave even starts.
+  int chunk = e->steps_per_launch;
+  if (chunk <= 0) {
+    int max_clusters = 0;
+    HM_TRY(decode_persistent_max_clusters(&max_clusters));
+    chunk = ceil_div(rows, p.rows_per_cluster) <= max_clusters ? max_len : 16;
+  }
   bool done = false;
   int poll_idx = 0;
   for (int s0 = 0; s0 < max_len && !done; s0 += chunk, ++poll_idx) {
@@ -1258,7 +1267,7 @@ HM_API int hmocr_set_option(hmocr_engine* e, const char* name, int value) {
     HM_CHECK(value == 0 || value == 1, "decode_impl must be 0 (persistent cluster kernel) or 1 (step graph)");
     e->decode_impl = value;
   } else if (n == "steps_per_launch") {
-    HM_CHECK(value >= 1 && value <= 256, "steps_per_launch must be in [1,256]");
+    HM_CHECK(value >= 0 && value <= 256, "steps_per_launch must be in [0,256] (0 = automatic)");
     e->steps_per_launch = value;
   } else if (n == "trace_step") {
     e->trace_step = value;

@@ -70,7 +70,9 @@ int hmocr_finalize_weights(hmocr_engine* e);
 /* Engine options (all have working defaults):
  *   "decode_impl"       0 = persistent thread-block-cluster decode kernel (default)
  *                       1 = one captured CUDA graph of per-layer kernels per step (kept for A/B tests)
- *   "steps_per_launch"  decode steps per persistent-kernel launch between all-finished polls (16)
+ *   "steps_per_launch"  decode steps per persistent-kernel launch; 0 (default) = automatic: one launch for the whole
+ *                       decode when all clusters of the batch are co-resident (the kernel stops by itself once every
+ *                       row has emitted eos), 16-step launches with a host poll in between for multi-wave batches
  *   "force_beam_kernel" 1 = run beam == 1 through the beam-search kernel (A/B test against greedy)
  *   "encoder_graph"     1 (default) = hmocr_generate* replay the encoder's ~95 kernels as one captured CUDA graph for
  *                       batches of up to 1024 images (GPU-side gain in the launch-bound regime of <= 32 images, host-side

@@ -246,7 +246,7 @@ def test_persistent_kernel_launch_chunking(model, golden_src, steps_per_launch):
     try:
         tok, steps, _ = model.generate(encoder_out=feats, max_len=40)
     finally:
-        model.set_option("steps_per_launch", 16)
+        model.set_option("steps_per_launch", 0)          # back to the automatic policy
     assert steps == ref_steps and torch.equal(tok, ref_tok)
 
 
