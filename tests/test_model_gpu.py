@@ -193,6 +193,22 @@ def test_generate_early_exit_and_padding(model, cfg, golden_src):
     assert model.last_decode_steps() == 5
 
 
+def test_kernel_stops_on_the_device_across_clusters(model, cfg, golden_src):
+    """Six clusters in one wave, rows that finish at different steps (the two golden rows that end at step 19,
+    repeated): every cluster - also those whose own rows finished long before - runs exactly until the step count the
+    reference's loop would reach, give or take the two steps the flag needs to travel, in ONE launch."""
+    feats = torch.from_numpy(golden_src["features"]).cuda()
+    feats = feats[[1, 2] * 23][:45].contiguous()                      # 45 rows = 5 full clusters + one of 5 rows
+    tokens, steps, _ = model.generate(encoder_out=feats, max_len=150)
+    torch.cuda.synchronize()
+    one, s1, _ = model.generate(encoder_out=feats[:2], max_len=150)
+    assert steps == s1 and torch.equal(tokens[:2], one)
+    assert torch.equal(tokens[::2], tokens[:1].expand(23, -1)) and torch.equal(tokens[1::2], tokens[1:2].expand(22, -1))
+    model.generate(encoder_out=feats, max_len=150)
+    torch.cuda.synchronize()
+    assert steps <= model.last_decode_steps() <= steps + 2
+
+
 def test_generate_is_batch_invariant(model, golden_src):
     imgs = _images(golden_src, 4).cuda()
     all_tok, steps, _ = model.generate(imgs, max_len=40)
